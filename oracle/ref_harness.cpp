@@ -1,0 +1,141 @@
+/*
+ * ref_harness.cpp — C-ABI window onto the UNMODIFIED reference solver classes.
+ *
+ * TEST INFRASTRUCTURE ONLY (see oracle/cg_oracle.c header).  This file contains no reference
+ * code: it #includes the reference's LAM.hpp from where it lies under /root/reference (the path
+ * is given on the compiler command line by oracle/Makefile) and is compiled into
+ * oracle/_ref/libref_harness.so, which is git-ignored and travels to the GPU box prebuilt.
+ *
+ * Why a harness: ConjugateGradient_CPU_MPI_OMP::save_result_to_file writes the rhs instead of
+ * the solution (MPI_OMP.hpp:436-439), and neither CPU class can be fed an in-memory system, so
+ * the only way to observe the reference's x and to time its solve() without file I/O is to
+ * reach its private members.  `#define private public` does that without touching the sources.
+ */
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <iostream>
+#include <string>
+#include <unistd.h>
+#include <fcntl.h>
+#include <omp.h>
+
+#define private public
+#include "LAM.hpp"
+#undef private
+
+namespace {
+
+/* The reference prints its results on stdout from inside solve(); capture them. */
+struct StdoutCapture {
+    int saved_fd = -1;
+    char path[64];
+    StdoutCapture()
+    {
+        fflush(stdout);
+        std::cout.flush();
+        std::strcpy(path, "/tmp/lamcg_ref_XXXXXX");
+        int fd = mkstemp(path);
+        saved_fd = dup(1);
+        dup2(fd, 1);
+        close(fd);
+    }
+    std::string finish()
+    {
+        fflush(stdout);
+        std::cout.flush();
+        dup2(saved_fd, 1);
+        close(saved_fd);
+        std::string out;
+        FILE *f = fopen(path, "rb");
+        if (f) {
+            char buf[4096];
+            size_t n;
+            while ((n = fread(buf, 1, sizeof buf, f)) > 0) out.append(buf, n);
+            fclose(f);
+        }
+        unlink(path);
+        return out;
+    }
+};
+
+} // namespace
+
+extern "C" {
+
+int ref_num_threads() { return omp_get_max_threads(); }
+void ref_set_threads(int n) { if (n > 0) omp_set_num_threads(n); }
+
+/*
+ * Generate mode through LAM::ConjugateGradient_CPU_MPI_OMP<double> (1 rank via the mpi shim):
+ * generate_matrix(n,n), generate_rhs(), solve(max_iters, rel_err).  Outputs: x (n doubles,
+ * nullable), iteration count exactly as the class prints it (max_iters+1 when not converged),
+ * relative residual parsed from the class's own CSV fields, and wall seconds of solve() alone and
+ * of generate_matrix() alone.  Returns solve()'s bool (1/0), -1 on parse failure.
+ */
+int ref_gen_solve(size_t n, int max_iters, double rel_err, double *x_out, int *iters_out,
+                  double *rel_out, double *solve_seconds, double *gen_seconds)
+{
+    LAM::ConjugateGradient_CPU_MPI_OMP<double> cg;
+    StdoutCapture cap;
+    double t0 = omp_get_wtime();
+    cg.generate_matrix(n, n);
+    double t1 = omp_get_wtime();
+    cg.generate_rhs();
+    double t2 = omp_get_wtime();
+    bool ok = cg.solve(max_iters, rel_err);
+    double t3 = omp_get_wtime();
+    std::string out = cap.finish();
+    if (gen_seconds) *gen_seconds = t1 - t0;
+    if (solve_seconds) *solve_seconds = t3 - t2;
+    /* stdout so far: "<n>,<avg_gemv>,<avg_iter>,<iters>,<rel>," */
+    unsigned long nn = 0;
+    double g = 0, it = 0, rel = 0;
+    int iters = 0;
+    int got = sscanf(out.c_str(), "%lu,%lf,%lf,%d,%lf,", &nn, &g, &it, &iters, &rel);
+    if (x_out) std::memcpy(x_out, cg._x, n * sizeof(double));
+    delete[] cg._matrix; delete[] cg._rhs; delete[] cg._x; delete[] cg._r; delete[] cg._Ap; delete[] cg._p;
+    delete[] cg._sendcounts; delete[] cg._displs;
+    if (got != 5) return -1;
+    if (iters_out) *iters_out = iters;
+    if (rel_out) *rel_out = rel;
+    return ok ? 1 : 0;
+}
+
+/*
+ * In-memory system through LAM::ConjugateGradient_CPU_OMP<double>::solve.  The class normally
+ * fills its members in load_matrix_from_file/load_rhs_from_file (OMP.hpp:93-197); here they are
+ * pointed at the caller's buffers instead, which leaves solve() itself untouched.
+ */
+int ref_omp_solve(const double *A, const double *b, size_t n, int max_iters, double rel_err,
+                  double *x_out, int *iters_out, double *rel_out, double *solve_seconds)
+{
+    LAM::ConjugateGradient_CPU_OMP<double> cg;
+    cg._num_rows = n;
+    cg._num_cols = n;
+    cg._matrix = const_cast<double *>(A);
+    cg._rhs = const_cast<double *>(b);
+    cg._x = x_out;
+    cg._r = new double[n];
+    cg._p = new double[n];
+    cg._Ap = new double[n];
+    StdoutCapture cap;
+    double t0 = omp_get_wtime();
+    bool ok = cg.solve(max_iters, rel_err);
+    double t1 = omp_get_wtime();
+    std::string out = cap.finish();
+    if (solve_seconds) *solve_seconds = t1 - t0;
+    delete[] cg._r; delete[] cg._p; delete[] cg._Ap;
+    int iters = 0;
+    double rel = 0;
+    int got;
+    if (ok) got = sscanf(out.c_str(), "Converged in %d iterations, relative error is %lf", &iters, &rel);
+    else got = sscanf(out.c_str(), "Did not converge in %d iterations, relative error is %lf", &iters, &rel);
+    if (got != 2) return -1;
+    if (iters_out) *iters_out = iters;
+    if (rel_out) *rel_out = rel;
+    return ok ? 1 : 0;
+}
+
+} // extern "C"
