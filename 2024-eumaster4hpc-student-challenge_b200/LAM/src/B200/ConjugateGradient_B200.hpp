@@ -1,0 +1,152 @@
+// ConjugateGradient_B200.hpp — the one concrete solver of this build.
+//
+// Public surface = the reference's distributed GPU classes
+// (GPU/distributed/ConjugateGradient_MultiGPUS_CUDA_NCCL.cuh:24-55: solve, load_matrix_from_file,
+// load_rhs_from_file, save_result_to_file, generate_matrix, generate_rhs, get_num_rows,
+// get_num_cols) plus the original challenge signature solve(A, b, x, size, max_iters, rel_error)
+// that survives as a comment in test/test_CG_CPU_OMP.cpp:76-79.  Every method is a thin call into
+// the C ABI of include/lamcg.h; all arithmetic happens in liblamcg.so on the GPU.  Behaviour kept
+// from the reference: bool returns, messages on stderr, no exceptions, solve() == false when not
+// converged, get_num_rows() == LOCAL rows, iteration count printed as max_iters+1 when not
+// converged (MPI_OMP.hpp:125).
+#pragma once
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <iostream>
+#include <type_traits>
+
+#include "lamcg.h"
+
+#include "../ConjugateGradient.hpp"
+#include "RankWorld.hpp"
+
+namespace LAM {
+
+enum class Report {
+    Quiet, // print nothing
+    Text,  // "Converged in %d iterations, ..." like ConjugateGradient_CPU_OMP::solve (OMP.hpp:80-90)
+    Csv    // "n," from load/generate and "avg_gemv,avg_iter,iters,rel," from solve, like the
+           // distributed classes (MPI_OMP.hpp:203-205,122-127); rank 0 only
+};
+
+template <typename FloatingType>
+class ConjugateGradient_B200 : public ConjugateGradient<FloatingType> {
+    static_assert(std::is_same<FloatingType, double>::value,
+                  "the B200 hot path is fp64 (the reference drivers instantiate <double>); fp32 is a later row");
+
+public:
+    explicit ConjugateGradient_B200(int device = 0, int rank = 0, int nranks = 1, Report report = Report::Text)
+        : rank_(rank), nranks_(nranks), report_(report)
+    {
+        const int rc = lamcg_create_ranked(&h_, device, rank, nranks);
+        if (rc != LAMCG_OK) {
+            std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
+            h_ = nullptr;
+        }
+    }
+    // One rank per process of a RankWorld: device = rank, communicator bootstrapped over the world.
+    ConjugateGradient_B200(RankWorld &world, Report report) : ConjugateGradient_B200(world.rank(), world.rank(), world.size(), report)
+    {
+        init_comm(world);
+    }
+    ~ConjugateGradient_B200() override { lamcg_destroy(h_); }
+    ConjugateGradient_B200(const ConjugateGradient_B200 &) = delete;
+    ConjugateGradient_B200 &operator=(const ConjugateGradient_B200 &) = delete;
+
+    bool ok() const { return h_ != nullptr; }
+    lamcg_t *handle() { return h_; }
+    void set_report(Report r) { report_ = r; }
+    bool set_option(const char *key, long long v) { return h_ && check(lamcg_set_option(h_, key, v)); }
+
+    // NCCL bootstrap; returns seconds spent (the reference times and prints it, NCCL.cu:306-334).
+    double init_comm(RankWorld &world)
+    {
+        if (!h_ || world.size() == 1) return 0.0;
+        const auto t0 = std::chrono::steady_clock::now();
+        unsigned char id[LAMCG_NCCL_ID_BYTES] = {0};
+        if (world.rank() == 0 && lamcg_comm_nccl_unique_id(id) != LAMCG_OK) std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
+        world.bcast(id, sizeof id, 0);
+        check(lamcg_comm_init_nccl(h_, id));
+        world.barrier();
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    }
+
+    // ---- reference interface -------------------------------------------------------------------
+    bool solve(int max_iters, FloatingType rel_error) override
+    {
+        if (!h_ || !check(lamcg_solve(h_, max_iters, rel_error, &last_))) return false;
+        double gemv_ms = 0.0;
+        if (report_ == Report::Csv) lamcg_time_gemv(h_, 1, 3, &gemv_ms);
+        if (rank_ == 0) {
+            if (report_ == Report::Csv) {
+                const int its = last_.iterations_run > 0 ? last_.iterations_run : 1;
+                std::cout << gemv_ms * 1e-3 << "," << last_.solve_seconds / its << "," << last_.iterations << ","
+                          << last_.rel_residual << ",";
+            } else if (report_ == Report::Text) {
+                if (last_.converged)
+                    std::printf("Converged in %d iterations, relative error is %e\n", last_.iterations, last_.rel_residual);
+                else
+                    std::printf("Did not converge in %d iterations, relative error is %e\n", max_iters, last_.rel_residual);
+            }
+        }
+        return last_.converged != 0;
+    }
+
+    bool load_matrix_from_file(const char *filename) override
+    {
+        if (!h_ || !check(lamcg_load_matrix(h_, filename))) return false;
+        print_n();
+        return true;
+    }
+    bool load_rhs_from_file(const char *filename) override { return h_ && check(lamcg_load_rhs(h_, filename)); }
+    bool save_result_to_file(const char *filename) const override { return h_ && check(lamcg_save_solution(h_, filename)); }
+
+    virtual bool generate_matrix(size_t num_rows, size_t num_cols)
+    {
+        if (!h_ || !check(lamcg_generate_matrix(h_, num_rows, num_cols))) return false;
+        print_n();
+        return true;
+    }
+    virtual bool generate_rhs() { return h_ && check(lamcg_generate_rhs(h_)); }
+
+    size_t get_num_rows() const { return info().local_rows; }
+    size_t get_num_cols() const { return info().n; }
+
+    // ---- original challenge signature: caller-owned buffers (host or device pointers) ------------
+    bool solve(const FloatingType *A, const FloatingType *b, FloatingType *x, size_t size, int max_iters, FloatingType rel_error)
+    {
+        if (!h_ || !check(lamcg_set_matrix(h_, A, size, 0)) || !check(lamcg_set_rhs(h_, b, size))) return false;
+        const bool converged = solve(max_iters, rel_error);
+        if (!check(lamcg_get_solution(h_, x))) return false;
+        return converged;
+    }
+
+    const lamcg_result &last_result() const { return last_; }
+    lamcg_info info() const
+    {
+        lamcg_info i{};
+        if (h_) lamcg_get_info(h_, &i);
+        return i;
+    }
+
+private:
+    bool check(int rc) const
+    {
+        if (rc == LAMCG_OK) return true;
+        if (rank_ == 0) std::fprintf(stderr, "%s\n", lamcg_last_error(h_));
+        return false;
+    }
+    void print_n() const
+    {
+        if (report_ == Report::Csv && rank_ == 0) std::cout << info().n << ",";
+    }
+
+    lamcg_t *h_ = nullptr;
+    int rank_ = 0, nranks_ = 1;
+    Report report_;
+    lamcg_result last_{};
+};
+
+} // namespace LAM

@@ -1,0 +1,338 @@
+"""B200-native dense Conjugate Gradient — Python host mirror of the reference's solver interface.
+
+The product is ``liblamcg.so`` (hand-written sm_100a CUDA kernels behind the C ABI declared in
+``include/lamcg.h``).  This module is only a thin ctypes binding plus ``ConjugateGradient_B200``,
+a class with the same method names, argument meaning and bool/print behaviour as the reference's
+``LAM::ConjugateGradient<T>`` hierarchy (challenge/main/LAM/src/ConjugateGradient.hpp:9-28,
+CPU/ConjugateGradient_CPU_MPI_OMP.hpp:19-69), so tests read like runs of the reference drivers.
+The reference itself is C++; the C++ twin of this class is ``LAM/src/B200/ConjugateGradient_B200.hpp``.
+
+There is no CPU fallback: importing works anywhere (so the CPU test-suite can check the ABI), but
+creating a solver without a CUDA device raises ``LamcgError``.
+
+The directory name is not a valid Python identifier; import it with
+``importlib.import_module("2024-eumaster4hpc-student-challenge_b200")`` or via ``lamcg_b200.py``
+at the repository root.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+LIB_PATH = os.path.join(HERE, "liblamcg.so")
+HEADER_PATH = os.path.join(REPO, "include", "lamcg.h")
+
+NCCL_ID_BYTES = 128
+PEER_HANDLE_BYTES = 128
+
+STATUS = {0: "OK", -1: "INVALID", -2: "CUDA", -3: "IO", -4: "SHAPE", -5: "NOMEM", -6: "COMM", -7: "STATE", -8: "DEVICE"}
+
+
+class LamcgError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"lamcg error {code} ({STATUS.get(code, '?')}): {message}")
+        self.code = code
+        self.message = message
+
+
+class lamcg_result(ctypes.Structure):
+    _fields_ = [("converged", ctypes.c_int), ("iterations", ctypes.c_int), ("rel_residual", ctypes.c_double),
+                ("solve_seconds", ctypes.c_double), ("gemv_seconds", ctypes.c_double),
+                ("iterations_run", ctypes.c_int), ("kernel_launches", ctypes.c_int)]
+
+
+class lamcg_info(ctypes.Structure):
+    _fields_ = [("n", ctypes.c_size_t), ("local_rows", ctypes.c_size_t), ("row_offset", ctypes.c_size_t),
+                ("lda", ctypes.c_size_t), ("rank", ctypes.c_int), ("nranks", ctypes.c_int), ("device", ctypes.c_int),
+                ("sm_count", ctypes.c_int), ("comm_mode", ctypes.c_int), ("has_matrix", ctypes.c_int),
+                ("has_rhs", ctypes.c_int), ("gemv_variant", ctypes.c_int), ("gemv_grid", ctypes.c_int),
+                ("gemv_block", ctypes.c_int), ("gemv_smem_bytes", ctypes.c_int)]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile liblamcg.so in tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", HERE, "lib"], capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("building liblamcg.so failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stdout)
+    return LIB_PATH
+
+
+_lib = None
+_vp, _cp, _dp = ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double)
+
+# name -> (restype, argtypes): must list every symbol include/lamcg.h declares (tests check that).
+_SIGNATURES = {
+    "lamcg_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
+    "lamcg_create_ranked": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "lamcg_destroy": (None, [_vp]),
+    "lamcg_last_error": (_cp, [_vp]),
+    "lamcg_version": (_cp, []),
+    "lamcg_set_option": (ctypes.c_int, [_vp, _cp, ctypes.c_longlong]),
+    "lamcg_get_info": (ctypes.c_int, [_vp, ctypes.POINTER(lamcg_info)]),
+    "lamcg_comm_nccl_unique_id": (ctypes.c_int, [_vp]),
+    "lamcg_comm_init_nccl": (ctypes.c_int, [_vp, _vp]),
+    "lamcg_comm_peer_export": (ctypes.c_int, [_vp, ctypes.c_size_t, _vp]),
+    "lamcg_comm_init_peer": (ctypes.c_int, [_vp, _vp]),
+    "lamcg_generate_matrix": (ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.c_size_t]),
+    "lamcg_generate_rhs": (ctypes.c_int, [_vp]),
+    "lamcg_load_matrix": (ctypes.c_int, [_vp, _cp]),
+    "lamcg_load_rhs": (ctypes.c_int, [_vp, _cp]),
+    "lamcg_set_matrix": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int]),
+    "lamcg_set_rhs": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "lamcg_solve": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.POINTER(lamcg_result)]),
+    "lamcg_get_residual_history": (ctypes.c_int, [_vp, _dp, ctypes.c_int]),
+    "lamcg_get_solution_local": (ctypes.c_int, [_vp, _dp]),
+    "lamcg_get_solution": (ctypes.c_int, [_vp, _dp]),
+    "lamcg_save_solution": (ctypes.c_int, [_vp, _cp]),
+    "lamcg_gemv": (ctypes.c_int, [_vp, _dp, _dp, _dp]),
+    "lamcg_time_gemv": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp]),
+    "lamcg_time_stream_read": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp, _dp]),
+}
+
+
+def lib() -> ctypes.CDLL:
+    """Load liblamcg.so (fails loudly if it has not been built: there is no fallback path)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LamcgError(-2, f"{LIB_PATH} is missing — run `python -c 'import __graft_entry__ as g; g.build()'` "
+                                 "(the CUDA library is the only implementation; there is no CPU fallback)")
+        L = ctypes.CDLL(LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _as_f64(a, name: str) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=np.float64)
+    if arr.size == 0:
+        raise ValueError(f"{name} is empty")
+    return arr
+
+
+class Solver:
+    """Direct, exception-raising wrapper over one ``lamcg_t`` (one rank == one GPU)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1):
+        self._L = lib()
+        h = _vp()
+        rc = self._L.lamcg_create_ranked(ctypes.byref(h), device, rank, nranks)
+        if rc != 0:
+            raise LamcgError(rc, (self._L.lamcg_last_error(None) or b"").decode())
+        self._h = h
+        self.rank, self.nranks, self.device = rank, nranks, device
+
+    # -- plumbing
+    def _ck(self, rc: int) -> int:
+        if rc < 0:
+            raise LamcgError(rc, (self._L.lamcg_last_error(self._h) or b"").decode())
+        return rc
+
+    def close(self) -> None:
+        if getattr(self, "_h", None):
+            self._L.lamcg_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def set_option(self, key: str, value: int) -> None:
+        self._ck(self._L.lamcg_set_option(self._h, key.encode(), int(value)))
+
+    @property
+    def info(self) -> lamcg_info:
+        out = lamcg_info()
+        self._ck(self._L.lamcg_get_info(self._h, ctypes.byref(out)))
+        return out
+
+    # -- comm bootstrap
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        buf = ctypes.create_string_buffer(NCCL_ID_BYTES)
+        rc = lib().lamcg_comm_nccl_unique_id(ctypes.cast(buf, _vp))
+        if rc != 0:
+            raise LamcgError(rc, (lib().lamcg_last_error(None) or b"").decode())
+        return buf.raw
+
+    def comm_init_nccl(self, unique_id: bytes) -> None:
+        assert len(unique_id) == NCCL_ID_BYTES
+        buf = ctypes.create_string_buffer(unique_id, NCCL_ID_BYTES)
+        self._ck(self._L.lamcg_comm_init_nccl(self._h, ctypes.cast(buf, _vp)))
+
+    def comm_peer_export(self, n: int) -> bytes:
+        buf = ctypes.create_string_buffer(PEER_HANDLE_BYTES)
+        self._ck(self._L.lamcg_comm_peer_export(self._h, n, ctypes.cast(buf, _vp)))
+        return buf.raw
+
+    def comm_init_peer(self, all_handles: bytes) -> None:
+        assert len(all_handles) == PEER_HANDLE_BYTES * self.nranks
+        buf = ctypes.create_string_buffer(all_handles, len(all_handles))
+        self._ck(self._L.lamcg_comm_init_peer(self._h, ctypes.cast(buf, _vp)))
+
+    # -- system
+    def generate_matrix(self, rows: int, cols: int) -> None:
+        self._ck(self._L.lamcg_generate_matrix(self._h, rows, cols))
+
+    def generate_rhs(self) -> None:
+        self._ck(self._L.lamcg_generate_rhs(self._h))
+
+    def load_matrix(self, path: str) -> None:
+        self._ck(self._L.lamcg_load_matrix(self._h, os.fsencode(path)))
+
+    def load_rhs(self, path: str) -> None:
+        self._ck(self._L.lamcg_load_rhs(self._h, os.fsencode(path)))
+
+    def set_matrix(self, A, layout: int = 0) -> None:
+        """A: numpy array (host) or an object with ``data_ptr()`` (torch tensor, host or device)."""
+        if hasattr(A, "data_ptr"):
+            assert A.is_contiguous() and A.element_size() == 8
+            n = A.shape[1]
+            self._keep_A = A
+            self._ck(self._L.lamcg_set_matrix(self._h, _vp(A.data_ptr()), n, layout))
+        else:
+            arr = _as_f64(A, "A")
+            assert arr.ndim == 2
+            self._ck(self._L.lamcg_set_matrix(self._h, _vp(arr.ctypes.data), arr.shape[1], layout))
+
+    def set_rhs(self, b) -> None:
+        if hasattr(b, "data_ptr"):
+            assert b.is_contiguous() and b.element_size() == 8
+            self._ck(self._L.lamcg_set_rhs(self._h, _vp(b.data_ptr()), b.numel()))
+        else:
+            arr = _as_f64(b, "b").reshape(-1)
+            self._ck(self._L.lamcg_set_rhs(self._h, _vp(arr.ctypes.data), arr.size))
+
+    # -- solve
+    def solve(self, max_iters: int, rel_error: float) -> lamcg_result:
+        out = lamcg_result()
+        self._ck(self._L.lamcg_solve(self._h, int(max_iters), float(rel_error), ctypes.byref(out)))
+        return out
+
+    def residual_history(self, capacity: int | None = None) -> np.ndarray:
+        cap = capacity if capacity is not None else 1 << 22
+        buf = np.zeros(cap)
+        cnt = self._ck(self._L.lamcg_get_residual_history(self._h, buf.ctypes.data_as(_dp), cap))
+        return buf[:cnt].copy()
+
+    def solution_local(self) -> np.ndarray:
+        x = np.zeros(max(self.info.local_rows, 1))
+        self._ck(self._L.lamcg_get_solution_local(self._h, x.ctypes.data_as(_dp)))
+        return x[: self.info.local_rows]
+
+    def solution(self, out=None) -> np.ndarray:
+        """Whole x; ``out`` may be a pinned torch tensor / numpy array of n doubles."""
+        n = self.info.n
+        if out is None:
+            out = np.zeros(n)
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        self._ck(self._L.lamcg_get_solution(self._h, ctypes.cast(_vp(ptr), _dp)))
+        return out
+
+    def save_solution(self, path: str) -> None:
+        self._ck(self._L.lamcg_save_solution(self._h, os.fsencode(path)))
+
+    # -- hooks
+    def gemv(self, p) -> tuple[np.ndarray, float]:
+        p = _as_f64(p, "p").reshape(-1)
+        y = np.zeros(max(self.info.local_rows, 1))
+        d = ctypes.c_double()
+        self._ck(self._L.lamcg_gemv(self._h, p.ctypes.data_as(_dp), y.ctypes.data_as(_dp), ctypes.byref(d)))
+        return y[: self.info.local_rows], d.value
+
+    def time_gemv(self, warmup: int = 3, reps: int = 10) -> float:
+        ms = ctypes.c_double()
+        self._ck(self._L.lamcg_time_gemv(self._h, warmup, reps, ctypes.byref(ms)))
+        return ms.value
+
+    def time_stream_read(self, warmup: int = 2, reps: int = 5) -> tuple[float, float]:
+        ms, cs = ctypes.c_double(), ctypes.c_double()
+        self._ck(self._L.lamcg_time_stream_read(self._h, warmup, reps, ctypes.byref(ms), ctypes.byref(cs)))
+        return ms.value, cs.value
+
+
+class ConjugateGradient_B200:
+    """Mirror of the reference solver classes: bool returns, messages on stderr, never raises for
+    I/O or shape errors (OMP.hpp:98-118), ``solve`` returns False when not converged (OMP.hpp:86-90).
+
+    Same public methods as LAM::ConjugateGradient_CPU_MPI_OMP<double> (MPI_OMP.hpp:22-35)."""
+
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, verbose: bool = True):
+        self._s = Solver(device, rank, nranks)
+        self.verbose = verbose
+        self.last_result: lamcg_result | None = None
+
+    @property
+    def solver(self) -> Solver:
+        return self._s
+
+    def _try(self, fn, *a) -> bool:
+        try:
+            fn(*a)
+            return True
+        except LamcgError as e:
+            if self._s.rank == 0:
+                print(e.message, file=sys.stderr)
+            return False
+
+    def load_matrix_from_file(self, filename: str) -> bool:
+        return self._try(self._s.load_matrix, filename)
+
+    def load_rhs_from_file(self, filename: str) -> bool:
+        return self._try(self._s.load_rhs, filename)
+
+    def save_result_to_file(self, filename: str) -> bool:
+        return self._try(self._s.save_solution, filename)
+
+    def generate_matrix(self, rows: int, cols: int) -> bool:
+        return self._try(self._s.generate_matrix, rows, cols)
+
+    def generate_rhs(self) -> bool:
+        return self._try(self._s.generate_rhs)
+
+    def get_num_rows(self) -> int:
+        return int(self._s.info.local_rows)  # local rows, like MPI_OMP.hpp:34
+
+    def get_num_cols(self) -> int:
+        return int(self._s.info.n)
+
+    def solve(self, max_iters: int, rel_error: float) -> bool:
+        res = self._s.solve(max_iters, rel_error)
+        self.last_result = res
+        if self.verbose and self._s.rank == 0:
+            if res.converged:
+                print("Converged in %d iterations, relative error is %e" % (res.iterations, res.rel_residual))
+            else:
+                print("Did not converge in %d iterations, relative error is %e" % (max_iters, res.rel_residual))
+        return bool(res.converged)
+
+    def solve_system(self, A, b, x, max_iters: int, rel_error: float) -> bool:
+        """The original challenge signature solve(A, b, x, size, max_iters, rel_error)
+        (test/test_CG_CPU_OMP.cpp:76-79) on caller-owned buffers; x is filled in place."""
+        self._s.set_matrix(A)
+        self._s.set_rhs(b)
+        ok = self.solve(max_iters, rel_error)
+        self._s.solution(out=x)
+        return ok
+
+    def close(self) -> None:
+        self._s.close()

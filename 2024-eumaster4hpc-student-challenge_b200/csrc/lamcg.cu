@@ -1,0 +1,926 @@
+// lamcg.cu — host side of liblamcg.so: the rank object, the device-resident CG loop (stream or
+// CUDA-graph driven), multi-GPU plumbing, file ingest, and the extern "C" surface of
+// include/lamcg.h.  No CPU fallback anywhere: every compute entry point needs the GPU.
+#include <algorithm>
+#include <cerrno>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <cuda_runtime.h>
+
+#include "../../include/lamcg.h"
+#include "lamcg_kernels.cuh"
+#include "nccl_dyn.h"
+
+using namespace lamcgk;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr int kVecThreads = 256;
+constexpr int kCommNone = 0, kCommNccl = 1, kCommPeer = 2;
+constexpr int kLoopAuto = 0, kLoopStream = 1, kLoopGraph = 2;
+
+struct GemvPlan {
+    int variant = 0;
+    void (*kernel)(GemvArgs) = nullptr;
+    int grid = 0, block = 0;
+    size_t smem = 0;
+    int rows_per_pass = 1;
+};
+
+long long env_ll(const char *key, long long dflt)
+{
+    std::string name = "LAMCG_";
+    for (const char *c = key; *c; ++c) name.push_back((char)toupper(*c));
+    const char *v = getenv(name.c_str());
+    return v && *v ? atoll(v) : dflt;
+}
+
+} // namespace
+
+struct lamcg {
+    int device = 0, rank = 0, nranks = 1, sm_count = 0;
+    cudaStream_t stream = nullptr;
+    size_t n = 0, local_rows = 0, row_offset = 0, lda = 0;
+    size_t alloc_n = 0;
+    double *A = nullptr, *b_full = nullptr, *x = nullptr, *r = nullptr, *Ap = nullptr, *p_full = nullptr;
+    double *x_full = nullptr; // gather target for get_solution (multi-rank), [lda]
+    double *partials = nullptr; // [2 * kMaxGrid]
+    double *hist = nullptr;
+    int hist_cap = 0;
+    DevState *st = nullptr;
+    DevState *h_st = nullptr; // pinned, 3 slots
+    bool has_matrix = false, has_rhs = false;
+
+    // options
+    long long opt_gemv_variant = 0, opt_loop_mode = 0, opt_chunk_iters = 16, opt_time_gemv = 0, opt_history = 1;
+    long long opt_gemv_ctas_per_sm = 0;
+
+    // comm
+    int comm_mode = kCommNone;
+    ncclComm_t nccl = nullptr;
+
+    // graph cache
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_chunk = 0;
+    int graph_variant = 0;
+    size_t graph_n = 0;
+
+    GemvPlan plan;
+    std::vector<cudaEvent_t> gemv_events;
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_ring[2] = {nullptr, nullptr};
+    int last_hist_count = 0;
+    std::string err;
+
+    int fail(int code, const char *fmt, ...)
+    {
+        char buf[1024];
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(buf, sizeof buf, fmt, ap);
+        va_end(ap);
+        err = buf;
+        return code;
+    }
+};
+
+#define CK(call)                                                                                      \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+    } while (0)
+
+#define NCK(call)                                                                                     \
+    do {                                                                                              \
+        ncclResult_t r_ = (call);                                                                     \
+        if (r_ != ncclSuccess) return h->fail(LAMCG_ERR_COMM, "%s failed: %s", #call, nccl_api().GetErrorString(r_)); \
+    } while (0)
+
+namespace {
+
+constexpr int kMaxGrid = 4096;
+
+template <int RB, int CB, int ST>
+bool plan_tma(lamcg *h, GemvPlan &p, int variant)
+{
+    using Cfg = GemvTmaCfg<RB, CB, ST>;
+    p.variant = variant;
+    p.kernel = gemv_tma_kernel<RB, CB, ST>;
+    p.block = Cfg::kThreads;
+    p.smem = Cfg::kSmemBytes;
+    p.rows_per_pass = RB;
+    int per_sm = 1;
+    p.grid = (int)std::min<size_t>((size_t)h->sm_count * per_sm, std::max<size_t>(1, h->local_rows));
+    return cudaFuncSetAttribute(gemv_tma_kernel<RB, CB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
+}
+
+template <int R, int U>
+bool plan_ldg(lamcg *h, GemvPlan &p, int variant)
+{
+    p.variant = variant;
+    p.kernel = gemv_ldg_kernel<R, U>;
+    p.block = kLdgWarps * 32;
+    p.smem = kLdgSmemBytes;
+    p.rows_per_pass = kLdgWarps * R;
+    int per_sm = h->opt_gemv_ctas_per_sm > 0 ? (int)h->opt_gemv_ctas_per_sm : 2;
+    size_t want = (h->local_rows + p.rows_per_pass - 1) / p.rows_per_pass;
+    p.grid = (int)std::min<size_t>((size_t)h->sm_count * per_sm, std::max<size_t>(1, want));
+    return cudaFuncSetAttribute(gemv_ldg_kernel<R, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
+}
+
+// Variant ids: 1x = ldg family, 2x = tma-ring family.  0 = auto.
+int make_plan(lamcg *h)
+{
+    int v = (int)h->opt_gemv_variant;
+    if (v == 0) v = 2;
+    bool ok = false;
+    GemvPlan p;
+    switch (v) {
+    case 1: ok = plan_ldg<4, 2>(h, p, v); break;
+    case 11: ok = plan_ldg<4, 4>(h, p, v); break;
+    case 12: ok = plan_ldg<2, 4>(h, p, v); break;
+    case 13: ok = plan_ldg<8, 2>(h, p, v); break;
+    case 14: ok = plan_ldg<2, 8>(h, p, v); break;
+    case 2: ok = plan_tma<16, 256, 6>(h, p, v); break;
+    case 21: ok = plan_tma<8, 256, 12>(h, p, v); break;
+    case 22: ok = plan_tma<32, 128, 6>(h, p, v); break;
+    case 23: ok = plan_tma<16, 512, 3>(h, p, v); break;
+    case 24: ok = plan_tma<16, 128, 12>(h, p, v); break;
+    case 25: ok = plan_tma<8, 512, 6>(h, p, v); break;
+    case 26: ok = plan_tma<16, 256, 4>(h, p, v); break;
+    case 27: ok = plan_tma<16, 256, 3>(h, p, v); break;
+    default: return h->fail(LAMCG_ERR_INVALID, "unknown gemv_variant %d", v);
+    }
+    if (!ok) return h->fail(LAMCG_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed for gemv variant %d: %s", v,
+                            cudaGetErrorString(cudaGetLastError()));
+    if (p.grid > kMaxGrid) p.grid = kMaxGrid;
+    h->plan = p;
+    return LAMCG_OK;
+}
+
+void free_system(lamcg *h)
+{
+    cudaSetDevice(h->device);
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaFree(h->A); cudaFree(h->b_full); cudaFree(h->x); cudaFree(h->r); cudaFree(h->Ap);
+    cudaFree(h->p_full); cudaFree(h->x_full);
+    h->A = h->b_full = h->x = h->r = h->Ap = h->p_full = h->x_full = nullptr;
+    h->alloc_n = 0;
+    h->has_matrix = h->has_rhs = false;
+}
+
+// Row partition of the reference (MPI_OMP.hpp:175-184): n/P rows each, remainder to the last rank.
+void partition(size_t n, int nranks, int rank, size_t *rows, size_t *offset)
+{
+    const size_t base = n / (size_t)nranks;
+    *offset = base * (size_t)rank;
+    *rows = base + (rank == nranks - 1 ? n % (size_t)nranks : 0);
+}
+
+int alloc_system(lamcg *h, size_t n)
+{
+    if (n == 0) return h->fail(LAMCG_ERR_SHAPE, "empty system");
+    if (h->alloc_n == n && h->A) return LAMCG_OK;
+    free_system(h);
+    CK(cudaSetDevice(h->device));
+    h->n = n;
+    partition(n, h->nranks, h->rank, &h->local_rows, &h->row_offset);
+    h->lda = (n + 15) / 16 * 16; // rows start on 128-byte boundaries; pad columns are zero
+    const size_t rows_alloc = std::max<size_t>(h->local_rows, 1);
+    cudaError_t e = cudaMalloc(&h->A, rows_alloc * h->lda * sizeof(double));
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return h->fail(LAMCG_ERR_NOMEM, "cudaMalloc of the %zu x %zu row block (%.2f GB) failed: %s", h->local_rows, h->lda,
+                       rows_alloc * h->lda * 8.0 / 1e9, cudaGetErrorString(e));
+    }
+    CK(cudaMalloc(&h->b_full, h->lda * sizeof(double)));
+    CK(cudaMalloc(&h->p_full, h->lda * sizeof(double)));
+    CK(cudaMalloc(&h->x_full, h->lda * sizeof(double)));
+    CK(cudaMalloc(&h->x, rows_alloc * sizeof(double)));
+    CK(cudaMalloc(&h->r, rows_alloc * sizeof(double)));
+    CK(cudaMalloc(&h->Ap, rows_alloc * sizeof(double)));
+    CK(cudaMemsetAsync(h->b_full, 0, h->lda * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->p_full, 0, h->lda * sizeof(double), h->stream));
+    CK(cudaMemsetAsync(h->x, 0, rows_alloc * sizeof(double), h->stream));
+    h->alloc_n = n;
+    int rc = make_plan(h);
+    if (rc != LAMCG_OK) return rc;
+    return LAMCG_OK;
+}
+
+GemvArgs gemv_args(lamcg *h, int check_done)
+{
+    GemvArgs g;
+    g.A = h->A;
+    g.p = h->p_full;
+    g.Ap = h->Ap;
+    g.partials = h->partials;
+    g.st = h->st;
+    g.rows = (long long)h->local_rows;
+    g.lda = (long long)h->lda;
+    g.row_offset = (long long)h->row_offset;
+    g.check_done = check_done;
+    return g;
+}
+
+int launch_gemv(lamcg *h, int check_done)
+{
+    GemvArgs g = gemv_args(h, check_done);
+    h->plan.kernel<<<h->plan.grid, h->plan.block, h->plan.smem, h->stream>>>(g);
+    CK(cudaGetLastError());
+    return LAMCG_OK;
+}
+
+int vec_grid(lamcg *h)
+{
+    size_t want = (h->local_rows + kVecThreads - 1) / kVecThreads;
+    return (int)std::min<size_t>(std::max<size_t>(want, 1), (size_t)h->sm_count * 4);
+}
+
+VecArgs vec_args(lamcg *h, int par)
+{
+    VecArgs v;
+    v.st = h->st;
+    const bool multi = h->comm_mode == kCommNccl;
+    v.pAp_src = multi ? &h->st->pAp : &h->st->pAp_local;
+    v.rrn_src = multi ? &h->st->rrn : &h->st->rrn_local;
+    v.x = h->x;
+    v.r = h->r;
+    v.Ap = h->Ap;
+    v.p_full = h->p_full;
+    v.partials = h->partials + kMaxGrid;
+    v.hist = h->opt_history ? h->hist : nullptr;
+    v.rows = (long long)h->local_rows;
+    v.row_offset = (long long)h->row_offset;
+    v.par = par;
+    return v;
+}
+
+// All-gather of the p slices with the reference partition: P equal slices of n/P plus the
+// remainder owned by the last rank (MPI_OMP.hpp:505 gathers Ap the same way with Allgatherv).
+int allgather_vec(lamcg *h, double *full)
+{
+    NcclApi &N = nccl_api();
+    const size_t base = h->n / (size_t)h->nranks;
+    const size_t tail = h->n % (size_t)h->nranks;
+    if (base > 0) NCK(N.AllGather(full + h->row_offset, full, base, ncclDouble, h->nccl, h->stream));
+    if (tail > 0) {
+        double *t = full + base * (size_t)h->nranks;
+        NCK(N.Broadcast(t, t, tail, ncclDouble, h->nranks - 1, h->nccl, h->stream));
+    }
+    return LAMCG_OK;
+}
+
+// One CG iteration enqueued on h->stream (also the body captured into the CUDA graph).
+int enqueue_iteration(lamcg *h, int par, cudaEvent_t ev0, cudaEvent_t ev1, int *launches)
+{
+    NcclApi &N = nccl_api();
+    if (ev0) CK(cudaEventRecord(ev0, h->stream));
+    int rc = launch_gemv(h, 1);
+    if (rc != LAMCG_OK) return rc;
+    if (ev1) CK(cudaEventRecord(ev1, h->stream));
+    if (h->comm_mode == kCommNccl)
+        NCK(N.AllReduce(&h->st->pAp_local, &h->st->pAp, 1, ncclDouble, ncclSum, h->nccl, h->stream));
+    VecArgs v = vec_args(h, par);
+    const int vg = vec_grid(h);
+    update_xr_kernel<<<vg, kVecThreads, 0, h->stream>>>(v);
+    CK(cudaGetLastError());
+    if (h->comm_mode == kCommNccl)
+        NCK(N.AllReduce(&h->st->rrn_local, &h->st->rrn, 1, ncclDouble, ncclSum, h->nccl, h->stream));
+    update_p_kernel<<<vg, kVecThreads, 0, h->stream>>>(v);
+    CK(cudaGetLastError());
+    if (h->comm_mode == kCommNccl) {
+        rc = allgather_vec(h, h->p_full);
+        if (rc != LAMCG_OK) return rc;
+    }
+    *launches += 3;
+    return LAMCG_OK;
+}
+
+int build_graph(lamcg *h, int chunk)
+{
+    if (h->graph_exec && h->graph_chunk == chunk && h->graph_variant == h->plan.variant && h->graph_n == h->n) return LAMCG_OK;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+    int dummy = 0;
+    int rc = LAMCG_OK;
+    for (int i = 0; i < chunk && rc == LAMCG_OK; ++i) rc = enqueue_iteration(h, i & 1, nullptr, nullptr, &dummy);
+    cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
+    if (rc != LAMCG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    h->graph_chunk = chunk;
+    h->graph_variant = h->plan.variant;
+    h->graph_n = h->n;
+    return LAMCG_OK;
+}
+
+int ensure_hist(lamcg *h, int max_iters)
+{
+    if (!h->opt_history) return LAMCG_OK;
+    int want = std::max(max_iters, 1);
+    if (want > (1 << 22)) want = 1 << 22;
+    if (h->hist_cap >= want) return LAMCG_OK;
+    cudaFree(h->hist);
+    h->hist = nullptr;
+    h->hist_cap = 0;
+    CK(cudaMalloc(&h->hist, (size_t)want * sizeof(double)));
+    h->hist_cap = want;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; } // hist pointer is baked in
+    return LAMCG_OK;
+}
+
+int check_device_error(lamcg *h, const DevState &s)
+{
+    if (s.error != 0) return h->fail(LAMCG_ERR_DEVICE, "device reported fault %d (1 = mbarrier timeout, 2 = peer flag timeout)", s.error);
+    return LAMCG_OK;
+}
+
+// ---- file helpers ------------------------------------------------------------------------------
+int read_header(lamcg *h, int fd, const char *path, size_t *rows, size_t *cols)
+{
+    uint64_t hdr[2];
+    ssize_t got = pread(fd, hdr, sizeof hdr, 0);
+    if (got != (ssize_t)sizeof hdr) return h->fail(LAMCG_ERR_IO, "%s: short read of the 16-byte header", path);
+    *rows = (size_t)hdr[0];
+    *cols = (size_t)hdr[1];
+    return LAMCG_OK;
+}
+
+int pread_full(int fd, void *buf, size_t bytes, off_t off)
+{
+    char *c = static_cast<char *>(buf);
+    while (bytes > 0) {
+        ssize_t got = pread(fd, c, bytes, off);
+        if (got < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        if (got == 0) return -1;
+        c += got;
+        off += got;
+        bytes -= (size_t)got;
+    }
+    return 0;
+}
+
+} // namespace
+
+// =================================================================================================
+// extern "C" surface
+// =================================================================================================
+extern "C" {
+
+const char *lamcg_version(void) { return "lamcg-b200 0.1 (sm_100a)"; }
+
+const char *lamcg_last_error(const lamcg_t *h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
+{
+    if (!out) return LAMCG_ERR_INVALID;
+    *out = nullptr;
+    if (nranks < 1 || rank < 0 || rank >= nranks) {
+        g_create_error = "invalid rank/nranks";
+        return LAMCG_ERR_INVALID;
+    }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device: ") + cudaGetErrorString(e) + " (this library has no CPU fallback)";
+        cudaGetLastError();
+        return LAMCG_ERR_CUDA;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device ordinal out of range";
+        return LAMCG_ERR_INVALID;
+    }
+    lamcg *h = new lamcg();
+    h->device = device;
+    h->rank = rank;
+    h->nranks = nranks;
+    auto bail = [&](const char *what, cudaError_t err) {
+        g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
+        delete h;
+        return (int)LAMCG_ERR_CUDA;
+    };
+    if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess) return bail("cudaGetDeviceProperties", e);
+    if (prop.major < 10) {
+        g_create_error = "this library is built for sm_100a (Blackwell B200) only";
+        delete h;
+        return LAMCG_ERR_CUDA;
+    }
+    h->sm_count = prop.multiProcessorCount;
+    if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
+    if ((e = cudaMalloc(&h->st, sizeof(DevState))) != cudaSuccess) return bail("cudaMalloc(state)", e);
+    if ((e = cudaMemset(h->st, 0, sizeof(DevState))) != cudaSuccess) return bail("cudaMemset(state)", e);
+    if ((e = cudaMalloc(&h->partials, 2 * kMaxGrid * sizeof(double))) != cudaSuccess) return bail("cudaMalloc(partials)", e);
+    if ((e = cudaMallocHost(&h->h_st, 3 * sizeof(DevState))) != cudaSuccess) return bail("cudaMallocHost(status)", e);
+    cudaEventCreate(&h->ev_start);
+    cudaEventCreate(&h->ev_stop);
+    cudaEventCreateWithFlags(&h->ev_ring[0], cudaEventDisableTiming);
+    cudaEventCreateWithFlags(&h->ev_ring[1], cudaEventDisableTiming);
+    h->opt_gemv_variant = env_ll("gemv_variant", 0);
+    h->opt_loop_mode = env_ll("loop_mode", 0);
+    h->opt_chunk_iters = env_ll("chunk_iters", 16);
+    h->opt_time_gemv = env_ll("time_gemv", 0);
+    h->opt_history = env_ll("history", 1);
+    h->opt_gemv_ctas_per_sm = env_ll("gemv_ctas_per_sm", 0);
+    *out = h;
+    return LAMCG_OK;
+}
+
+int lamcg_create(lamcg_t **out, int device) { return lamcg_create_ranked(out, device, 0, 1); }
+
+void lamcg_destroy(lamcg_t *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->nccl) nccl_api().CommDestroy(h->nccl);
+    free_system(h);
+    for (cudaEvent_t e : h->gemv_events) cudaEventDestroy(e);
+    cudaFree(h->hist);
+    cudaFree(h->st);
+    cudaFree(h->partials);
+    cudaFreeHost(h->h_st);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_stop) cudaEventDestroy(h->ev_stop);
+    if (h->ev_ring[0]) cudaEventDestroy(h->ev_ring[0]);
+    if (h->ev_ring[1]) cudaEventDestroy(h->ev_ring[1]);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int lamcg_set_option(lamcg_t *h, const char *key, long long value)
+{
+    if (!h || !key) return LAMCG_ERR_INVALID;
+    std::string k(key);
+    if (k == "gemv_variant") h->opt_gemv_variant = value;
+    else if (k == "loop_mode") h->opt_loop_mode = value;
+    else if (k == "chunk_iters") h->opt_chunk_iters = value;
+    else if (k == "time_gemv") h->opt_time_gemv = value;
+    else if (k == "history") h->opt_history = value;
+    else if (k == "gemv_ctas_per_sm") h->opt_gemv_ctas_per_sm = value;
+    else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
+    if (h->alloc_n) {
+        CK(cudaSetDevice(h->device));
+        return make_plan(h);
+    }
+    return LAMCG_OK;
+}
+
+int lamcg_get_info(const lamcg_t *h, lamcg_info *out)
+{
+    if (!h || !out) return LAMCG_ERR_INVALID;
+    out->n = h->n;
+    out->local_rows = h->local_rows;
+    out->row_offset = h->row_offset;
+    out->lda = h->lda;
+    out->rank = h->rank;
+    out->nranks = h->nranks;
+    out->device = h->device;
+    out->sm_count = h->sm_count;
+    out->comm_mode = h->comm_mode;
+    out->has_matrix = h->has_matrix;
+    out->has_rhs = h->has_rhs;
+    out->gemv_variant = h->plan.variant;
+    out->gemv_grid = h->plan.grid;
+    out->gemv_block = h->plan.block;
+    out->gemv_smem_bytes = (int)h->plan.smem;
+    return LAMCG_OK;
+}
+
+// ---- comm -----------------------------------------------------------------------------------
+int lamcg_comm_nccl_unique_id(void *id_out)
+{
+    if (!id_out) return LAMCG_ERR_INVALID;
+    const char *why = "";
+    if (!nccl_api().load(&why)) {
+        g_create_error = why;
+        return LAMCG_ERR_COMM;
+    }
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == LAMCG_NCCL_ID_BYTES, "ncclUniqueId size");
+    if (nccl_api().GetUniqueId(&id) != ncclSuccess) {
+        g_create_error = "ncclGetUniqueId failed";
+        return LAMCG_ERR_COMM;
+    }
+    memcpy(id_out, &id, sizeof id);
+    return LAMCG_OK;
+}
+
+int lamcg_comm_init_nccl(lamcg_t *h, const void *id)
+{
+    if (!h || !id) return LAMCG_ERR_INVALID;
+    if (h->nranks == 1) return LAMCG_OK;
+    const char *why = "";
+    if (!nccl_api().load(&why)) return h->fail(LAMCG_ERR_COMM, "%s", why);
+    CK(cudaSetDevice(h->device));
+    ncclUniqueId uid;
+    memcpy(&uid, id, sizeof uid);
+    NCK(nccl_api().CommInitRank(&h->nccl, h->nranks, uid, h->rank));
+    h->comm_mode = kCommNccl;
+    return LAMCG_OK;
+}
+
+int lamcg_comm_peer_export(lamcg_t *h, size_t, void *)
+{
+    if (!h) return LAMCG_ERR_INVALID;
+    return h->fail(LAMCG_ERR_INVALID, "peer exchange is not built into this version");
+}
+
+int lamcg_comm_init_peer(lamcg_t *h, const void *)
+{
+    if (!h) return LAMCG_ERR_INVALID;
+    return h->fail(LAMCG_ERR_INVALID, "peer exchange is not built into this version");
+}
+
+// ---- system ---------------------------------------------------------------------------------
+int lamcg_generate_matrix(lamcg_t *h, size_t rows, size_t cols)
+{
+    if (!h) return LAMCG_ERR_INVALID;
+    if (rows != cols) return h->fail(LAMCG_ERR_SHAPE, "Matrix has to be square");
+    int rc = alloc_system(h, rows);
+    if (rc != LAMCG_OK) return rc;
+    if (h->local_rows > 0) {
+        const long long total = (long long)h->local_rows * (long long)(h->lda / 2);
+        const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
+        generate_matrix_kernel<<<grid, 256, 0, h->stream>>>(h->A, (long long)h->local_rows, (long long)h->n, (long long)h->lda,
+                                                           (long long)h->row_offset);
+        CK(cudaGetLastError());
+    }
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_matrix = true;
+    h->has_rhs = false;
+    return LAMCG_OK;
+}
+
+int lamcg_generate_rhs(lamcg_t *h)
+{
+    if (!h) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "generate_rhs before a matrix exists");
+    CK(cudaSetDevice(h->device));
+    const int grid = (int)std::min<size_t>((h->lda + 255) / 256, (size_t)h->sm_count * 4);
+    fill_kernel<<<grid, 256, 0, h->stream>>>(h->b_full, (long long)h->n, (long long)h->lda, 1.0);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_rhs = true;
+    return LAMCG_OK;
+}
+
+int lamcg_set_matrix(lamcg_t *h, const double *A, size_t n, int layout)
+{
+    if (!h || !A) return LAMCG_ERR_INVALID;
+    int rc = alloc_system(h, n);
+    if (rc != LAMCG_OK) return rc;
+    const double *src = layout == 0 ? A + h->row_offset * n : A;
+    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * sizeof(double), h->stream));
+    if (h->local_rows > 0)
+        CK(cudaMemcpy2DAsync(h->A, h->lda * sizeof(double), src, n * sizeof(double), n * sizeof(double), h->local_rows,
+                             cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_matrix = true;
+    h->has_rhs = false;
+    return LAMCG_OK;
+}
+
+int lamcg_set_rhs(lamcg_t *h, const double *b, size_t n)
+{
+    if (!h || !b) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "set_rhs before a matrix exists");
+    if (n != h->n) return h->fail(LAMCG_ERR_SHAPE, "Size of right hand side does not match the matrix");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemcpyAsync(h->b_full, b, n * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->has_rhs = true;
+    return LAMCG_OK;
+}
+
+int lamcg_load_matrix(lamcg_t *h, const char *path)
+{
+    if (!h || !path) return LAMCG_ERR_INVALID;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return h->fail(LAMCG_ERR_IO, "Cannot open %s: %s", path, strerror(errno));
+    size_t rows = 0, cols = 0;
+    int rc = read_header(h, fd, path, &rows, &cols);
+    if (rc != LAMCG_OK) { close(fd); return rc; }
+    if (rows != cols) { close(fd); return h->fail(LAMCG_ERR_SHAPE, "Matrix has to be square"); }
+    struct stat sb;
+    if (fstat(fd, &sb) == 0 && (unsigned long long)sb.st_size < 16ull + (unsigned long long)rows * cols * 8ull) {
+        close(fd);
+        return h->fail(LAMCG_ERR_IO, "%s: file is shorter than its %zu x %zu header promises", path, rows, cols);
+    }
+    rc = alloc_system(h, rows);
+    if (rc != LAMCG_OK) { close(fd); return rc; }
+    const size_t n = h->n;
+    // chunked ingest: pread -> pinned double buffer -> async 2-D copy into the padded row block
+    const size_t row_bytes = n * sizeof(double);
+    size_t chunk_rows = std::max<size_t>(1, (size_t)(64u << 20) / row_bytes);
+    chunk_rows = std::min(chunk_rows, std::max<size_t>(h->local_rows, 1));
+    double *stage[2] = {nullptr, nullptr};
+    cudaEvent_t done[2];
+    auto cleanup = [&]() {
+        for (int i = 0; i < 2; ++i) { if (stage[i]) cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
+        close(fd);
+    };
+    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
+    for (int i = 0; i < 2; ++i) {
+        if (cudaMallocHost(&stage[i], chunk_rows * row_bytes) != cudaSuccess) {
+            cleanup();
+            return h->fail(LAMCG_ERR_NOMEM, "cudaMallocHost of the ingest buffer failed");
+        }
+    }
+    if (h->lda != n) cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * sizeof(double), h->stream);
+    int slot = 0;
+    for (size_t r = 0; r < h->local_rows; r += chunk_rows, slot ^= 1) {
+        const size_t nr = std::min(chunk_rows, h->local_rows - r);
+        cudaEventSynchronize(done[slot]);
+        const off_t off = (off_t)16 + (off_t)((h->row_offset + r) * row_bytes);
+        if (pread_full(fd, stage[slot], nr * row_bytes, off) != 0) {
+            cudaStreamSynchronize(h->stream);
+            cleanup();
+            return h->fail(LAMCG_ERR_IO, "%s: short read in rows %zu..%zu", path, h->row_offset + r, h->row_offset + r + nr);
+        }
+        cudaError_t e = cudaMemcpy2DAsync(h->A + r * h->lda, h->lda * sizeof(double), stage[slot], row_bytes, row_bytes, nr,
+                                          cudaMemcpyHostToDevice, h->stream);
+        if (e != cudaSuccess) {
+            cleanup();
+            return h->fail(LAMCG_ERR_CUDA, "cudaMemcpy2DAsync failed: %s", cudaGetErrorString(e));
+        }
+        cudaEventRecord(done[slot], h->stream);
+    }
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "matrix upload failed: %s", cudaGetErrorString(e));
+    h->has_matrix = true;
+    h->has_rhs = false;
+    return LAMCG_OK;
+}
+
+int lamcg_load_rhs(lamcg_t *h, const char *path)
+{
+    if (!h || !path) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "load_rhs before a matrix exists");
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return h->fail(LAMCG_ERR_IO, "Cannot open %s: %s", path, strerror(errno));
+    size_t rows = 0, cols = 0;
+    int rc = read_header(h, fd, path, &rows, &cols);
+    if (rc != LAMCG_OK) { close(fd); return rc; }
+    if (cols != 1) { close(fd); return h->fail(LAMCG_ERR_SHAPE, "The file does not contain a valid rhs"); }
+    if (rows != h->n) { close(fd); return h->fail(LAMCG_ERR_SHAPE, "Size of right hand side does not match the matrix"); }
+    std::vector<double> b(rows);
+    if (pread_full(fd, b.data(), rows * sizeof(double), 16) != 0) {
+        close(fd);
+        return h->fail(LAMCG_ERR_IO, "%s: short read", path);
+    }
+    close(fd);
+    return lamcg_set_rhs(h, b.data(), rows);
+}
+
+// ---- solve ----------------------------------------------------------------------------------
+int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
+{
+    if (!h) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix || !h->has_rhs) return h->fail(LAMCG_ERR_STATE, "solve needs a matrix and a right hand side");
+    if (h->nranks > 1 && h->comm_mode == kCommNone) return h->fail(LAMCG_ERR_STATE, "multi-rank solve before lamcg_comm_init_*");
+    CK(cudaSetDevice(h->device));
+    int rc = ensure_hist(h, max_iters);
+    if (rc != LAMCG_OK) return rc;
+
+    int loop_mode = (int)h->opt_loop_mode;
+    if (loop_mode == kLoopAuto) loop_mode = h->opt_time_gemv ? kLoopStream : kLoopGraph;
+    if (h->opt_time_gemv) loop_mode = kLoopStream;
+    int chunk = (int)std::max<long long>(2, h->opt_chunk_iters);
+    chunk += chunk & 1; // the parity double-buffering needs an even number of iterations per chunk
+    if (loop_mode == kLoopGraph) {
+        rc = build_graph(h, chunk);
+        if (rc != LAMCG_OK) return rc;
+    }
+    const bool time_gemv = h->opt_time_gemv != 0 && max_iters > 0;
+    if (time_gemv) {
+        const size_t need = 2 * (size_t)std::min(max_iters, 1 << 16);
+        while (h->gemv_events.size() < need) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->gemv_events.push_back(e);
+        }
+    }
+
+    InitArgs ia;
+    ia.st = h->st;
+    ia.b_full = h->b_full;
+    ia.x = h->x;
+    ia.r = h->r;
+    ia.Ap = h->Ap;
+    ia.p_full = h->p_full;
+    ia.n = (long long)h->n;
+    ia.lda = (long long)h->lda;
+    ia.rows = (long long)h->local_rows;
+    ia.row_offset = (long long)h->row_offset;
+    ia.eps = rel_error;
+    ia.max_iters = max_iters;
+    ia.hist_cap = h->opt_history ? h->hist_cap : 0;
+    init_solve_kernel<<<1, 1024, 0, h->stream>>>(ia);
+    CK(cudaGetLastError());
+    int launches = 1;
+
+    CK(cudaEventRecord(h->ev_start, h->stream));
+    int launched = 0, c = 0, timed_iters = 0;
+    bool stop = false;
+    while (launched < max_iters && !stop) {
+        if (loop_mode == kLoopGraph) {
+            CK(cudaGraphLaunch(h->graph_exec, h->stream));
+            launched += chunk;
+            launches += 3 * chunk;
+        } else {
+            for (int i = 0; i < chunk && launched < max_iters; ++i, ++launched) {
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                if (time_gemv && 2 * (size_t)launched + 1 < h->gemv_events.size()) {
+                    e0 = h->gemv_events[2 * launched];
+                    e1 = h->gemv_events[2 * launched + 1];
+                    timed_iters = launched + 1;
+                }
+                rc = enqueue_iteration(h, launched & 1, e0, e1, &launches);
+                if (rc != LAMCG_OK) return rc;
+            }
+        }
+        CK(cudaMemcpyAsync(&h->h_st[c & 1], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_ring[c & 1], h->stream));
+        if (c >= 1) { // one chunk of look-ahead: inspect the chunk before the one just enqueued
+            CK(cudaEventSynchronize(h->ev_ring[(c - 1) & 1]));
+            const DevState &s = h->h_st[(c - 1) & 1];
+            if (s.done || s.error) stop = true;
+        }
+        ++c;
+    }
+    CK(cudaEventRecord(h->ev_stop, h->stream));
+    CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "the CG loop faulted on the device: %s", cudaGetErrorString(se));
+    const DevState &s = h->h_st[2];
+    rc = check_device_error(h, s);
+    if (rc != LAMCG_OK) return rc;
+
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
+    double gemv_ms = 0.0;
+    if (time_gemv) {
+        const int cnt = std::min(timed_iters, s.iters_done);
+        for (int i = 0; i < cnt; ++i) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, h->gemv_events[2 * i], h->gemv_events[2 * i + 1]));
+            gemv_ms += t;
+        }
+    }
+    h->last_hist_count = h->opt_history ? std::min(s.iters_done, h->hist_cap) : 0;
+    if (out) {
+        out->converged = s.converged;
+        out->iterations = s.converged ? s.iters_done : (max_iters < 0 ? 1 : max_iters + 1);
+        out->rel_residual = std::sqrt(s.rr_final / s.bb);
+        out->solve_seconds = ms * 1e-3;
+        out->gemv_seconds = gemv_ms * 1e-3;
+        out->iterations_run = s.iters_done;
+        out->kernel_launches = launches;
+    }
+    return LAMCG_OK;
+}
+
+int lamcg_get_residual_history(lamcg_t *h, double *out, int capacity)
+{
+    if (!h || !out || capacity < 0) return LAMCG_ERR_INVALID;
+    const int cnt = std::min(capacity, h->last_hist_count);
+    if (cnt > 0) {
+        CK(cudaSetDevice(h->device));
+        CK(cudaMemcpyAsync(out, h->hist, (size_t)cnt * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaStreamSynchronize(h->stream));
+    }
+    return cnt;
+}
+
+int lamcg_get_solution_local(lamcg_t *h, double *x_local)
+{
+    if (!h || !x_local) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no system");
+    CK(cudaSetDevice(h->device));
+    if (h->local_rows) CK(cudaMemcpyAsync(x_local, h->x, h->local_rows * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LAMCG_OK;
+}
+
+int lamcg_get_solution(lamcg_t *h, double *x)
+{
+    if (!h || !x) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no system");
+    if (h->nranks == 1) return lamcg_get_solution_local(h, x);
+    CK(cudaSetDevice(h->device));
+    if (h->comm_mode != kCommNccl) return h->fail(LAMCG_ERR_STATE, "get_solution over ranks needs an initialised communicator");
+    if (h->local_rows)
+        CK(cudaMemcpyAsync(h->x_full + h->row_offset, h->x, h->local_rows * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    int rc = allgather_vec(h, h->x_full);
+    if (rc != LAMCG_OK) return rc;
+    CK(cudaMemcpyAsync(x, h->x_full, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LAMCG_OK;
+}
+
+int lamcg_save_solution(lamcg_t *h, const char *path)
+{
+    if (!h || !path) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no system");
+    std::vector<double> x(h->n);
+    int rc = lamcg_get_solution(h, x.data());
+    if (rc != LAMCG_OK) return rc;
+    if (h->rank != 0) return LAMCG_OK; // only rank 0 saves (MPI_OMP.hpp:426)
+    FILE *f = fopen(path, "wb");
+    if (!f) return h->fail(LAMCG_ERR_IO, "Cannot open output file %s: %s", path, strerror(errno));
+    const uint64_t hdr[2] = {(uint64_t)h->n, 1ull};
+    bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1 && fwrite(x.data(), sizeof(double), h->n, f) == h->n;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return h->fail(LAMCG_ERR_IO, "short write to %s", path);
+    return LAMCG_OK;
+}
+
+// ---- measurement / test hooks ----------------------------------------------------------------
+int lamcg_gemv(lamcg_t *h, const double *p, double *y_local, double *p_dot_y)
+{
+    if (!h || !p || !y_local) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
+    CK(cudaSetDevice(h->device));
+    CK(cudaMemsetAsync(h->p_full, 0, h->lda * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(h->p_full, p, h->n * sizeof(double), cudaMemcpyDefault, h->stream));
+    int rc = launch_gemv(h, 0);
+    if (rc != LAMCG_OK) return rc;
+    if (h->local_rows) CK(cudaMemcpyAsync(y_local, h->Ap, h->local_rows * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "GEMV faulted on the device: %s", cudaGetErrorString(se));
+    if (p_dot_y) *p_dot_y = h->h_st[2].pAp_local;
+    return check_device_error(h, h->h_st[2]);
+}
+
+int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch)
+{
+    if (!h || reps <= 0 || !ms_per_launch) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
+    CK(cudaSetDevice(h->device));
+    for (int i = 0; i < warmup; ++i) {
+        int rc = launch_gemv(h, 0);
+        if (rc != LAMCG_OK) return rc;
+    }
+    CK(cudaEventRecord(h->ev_start, h->stream));
+    for (int i = 0; i < reps; ++i) {
+        int rc = launch_gemv(h, 0);
+        if (rc != LAMCG_OK) return rc;
+    }
+    CK(cudaEventRecord(h->ev_stop, h->stream));
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "GEMV faulted on the device: %s", cudaGetErrorString(se));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
+    *ms_per_launch = (double)ms / reps;
+    return LAMCG_OK;
+}
+
+int lamcg_time_stream_read(lamcg_t *h, int warmup, int reps, double *ms_per_pass, double *checksum)
+{
+    if (!h || reps <= 0 || !ms_per_pass) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
+    CK(cudaSetDevice(h->device));
+    const long long count2 = (long long)(h->local_rows * h->lda / 2);
+    const int grid = std::min(h->sm_count * 4, kMaxGrid);
+    for (int i = 0; i < warmup; ++i) stream_read_kernel<<<grid, 512, 0, h->stream>>>(h->A, count2, h->partials);
+    CK(cudaEventRecord(h->ev_start, h->stream));
+    for (int i = 0; i < reps; ++i) stream_read_kernel<<<grid, 512, 0, h->stream>>>(h->A, count2, h->partials);
+    CK(cudaEventRecord(h->ev_stop, h->stream));
+    CK(cudaGetLastError());
+    std::vector<double> part(grid);
+    CK(cudaMemcpyAsync(part.data(), h->partials, grid * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
+    *ms_per_pass = (double)ms / reps;
+    if (checksum) {
+        double s = 0.0;
+        for (double v : part) s += v;
+        *checksum = s;
+    }
+    return LAMCG_OK;
+}
+
+} // extern "C"

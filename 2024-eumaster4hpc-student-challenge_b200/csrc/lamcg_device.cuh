@@ -1,0 +1,181 @@
+// lamcg_device.cuh — device-side state, PTX wrappers and small reductions shared by all kernels.
+// sm_100a only (TMA bulk copies, mbarrier, L2 cache-policy hints).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace lamcgk {
+
+// Everything one CG solve keeps on the device so that an iteration never visits the host.
+// The reference keeps alpha/beta/rr in device memory too (GPU/local/ConjugateGradient_GPU_CUDA.cu:246-254)
+// but copies rr and bb back every iteration for the stop test (:285-287); here the stop test,
+// the iteration counter and the `done` latch live next to them.
+//
+// rr[] and iter[] are double-buffered by iteration parity: inside one kernel every thread reads
+// slot [par] while a single thread writes slot [par^1], so no kernel both reads and writes the
+// same word and no extra "scalar" kernels (the reference's divide<<<1,1>>>, :273,:281) are needed.
+struct DevState {
+    double bb;         // rhs_module = b.b                      (OMP.hpp:65)
+    double rr[2];      // r.r entering the iteration, by parity (OMP.hpp:67,76)
+    double pAp_local;  // this rank's  sum p_i (Ap)_i  from the GEMV epilogue
+    double pAp;        // all-reduced value (multi-rank only; single rank reads pAp_local)
+    double rrn_local;  // this rank's  sum r_i r_i  after the update
+    double rrn;        // all-reduced value
+    double eps;        // rel_error
+    double rr_final;   // rr after the last executed iteration
+    double alpha_last, beta_last;
+    int iter[2];       // iterations executed so far, by parity
+    int max_iters;
+    int done;          // latch: once set every later kernel of the loop is a no-op
+    int converged;
+    int iters_done;
+    int error;         // 0 ok | 1 mbarrier timeout | 2 peer-flag timeout
+    int hist_cap;
+    unsigned int ticket_gemv;
+    unsigned int ticket_xr;
+    unsigned int ticket_misc;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+// make mbarrier.init visible to the async (TMA) proxy
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must end in a trap (sticky error reported by the host), never in
+// a hung GPU.  ~4e9 cycles is about two seconds.
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity, int *err_flag)
+{
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            *err_flag = 1;
+            __threadfence_system();
+            __trap();
+        }
+    }
+}
+
+__device__ __forceinline__ uint64_t l2_policy_evict_first()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_last()
+{
+    uint64_t p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+
+// TMA 1-D bulk copy global -> shared, completion counted in bytes on an mbarrier.
+// dst, src 16-byte aligned; bytes a multiple of 16.
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src, uint32_t bytes, uint64_t *bar, uint64_t policy)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+        ::"r"(smem_u32(dst_smem)), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+
+// 128-bit streaming load of two doubles: read-only path, no L1 allocation, L2 policy hint.
+__device__ __forceinline__ double2 ldg_stream_f64x2(const double *ptr, uint64_t policy)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(ptr), "l"(policy));
+    return v;
+}
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ int ld_volatile_int(const int *p) { return *(const volatile int *)p; }
+
+// ---------------------------------------------------------------------------------------------
+// Reductions.  All sums are evaluated in a fixed order (no floating-point atomics), so a solve is
+// bit-reproducible run to run for a given (n, ranks, grid).
+// Arithmetic mirrors the reference CPU build (baseline x86-64, no FMA contraction): a product is
+// rounded, then added (OMP.hpp:226,258).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double mul_add(double a, double b, double c) { return __dadd_rn(__dmul_rn(a, b), c); }
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-level sum for the vector kernels (blockDim.x a multiple of 32, <= 1024).  Result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double *scratch /* >= 32 doubles */)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) scratch[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < nw; ++w) s = __dadd_rn(s, scratch[w]);
+    __syncthreads();
+    return s;
+}
+
+// "Last CTA finishes": every CTA stores its partial, the CTA that draws the last ticket adds the
+// partials in index order and publishes the total.  Called by ONE full warp per CTA.
+__device__ __forceinline__ void grid_sum_publish(double cta_partial, double *partials, unsigned int *ticket,
+                                                 double *total_out, int lane)
+{
+    const int G = gridDim.x, bid = blockIdx.x;
+    int last = 0;
+    if (lane == 0) {
+        __stcg(&partials[bid], cta_partial);
+        __threadfence();
+        last = (atomicAdd(ticket, 1u) == (unsigned)(G - 1));
+    }
+    last = __shfl_sync(0xffffffffu, last, 0);
+    if (last) {
+        __threadfence();
+        double s = 0.0;
+        for (int i = lane; i < G; i += 32) s = __dadd_rn(s, __ldcg(&partials[i]));
+        s = warp_sum(s);
+        if (lane == 0) {
+            *total_out = s;
+            *ticket = 0u;
+        }
+    }
+}
+
+} // namespace lamcgk

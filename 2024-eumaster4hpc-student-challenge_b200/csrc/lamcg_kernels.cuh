@@ -1,0 +1,498 @@
+// lamcg_kernels.cuh — the CG hot path as hand-written sm_100a kernels.
+//
+//   K1  gemv_tma_kernel / gemv_ldg_kernel   Ap = A_local * p  (+ fused  p.Ap  partial)   HBM-bound
+//   K2  update_xr_kernel                     x += alpha p ; r -= alpha Ap ; r.r partial
+//   K3  update_p_kernel                      beta, stop test, p = r + beta p
+//       init_solve_kernel, generate_matrix_kernel, stream_read_kernel
+//
+// Reference functions replaced (all under /root/reference/challenge/main/LAM/src):
+//   gemv      CPU/ConjugateGradient_CPU_OMP.hpp:246-263, GPU/local/ConjugateGradient_GPU_CUDA.cu:170-223
+//   dot       OMP.hpp:219-231, GPU_CUDA.cu:64-114 (partialDot + reduce + cudaMalloc per call)
+//   axpby     OMP.hpp:233-244, GPU_CUDA.cu:130-168 (axpy / minusaxpy / xpby), divide :16-20
+//   stop test OMP.hpp:77, GPU_CUDA.cu:283-287 (two D2H copies + host sqrt per iteration)
+//   generator CPU/ConjugateGradient_CPU_MPI_OMP.hpp:237-247 (host loop + H2D in the GPU variants)
+#pragma once
+
+#include "lamcg_device.cuh"
+
+namespace lamcgk {
+
+struct GemvArgs {
+    const double *A;    // [rows][lda] row block of this rank, lda % 16 == 0, pad columns are zero
+    const double *p;    // [lda] full direction vector, zero padded
+    double *Ap;         // [rows]
+    double *partials;   // [grid] per-CTA partials of p.Ap
+    DevState *st;
+    long long rows;     // local rows
+    long long lda;      // padded columns
+    long long row_offset; // global index of local row 0 (p is indexed globally)
+    int check_done;     // 1 inside the solve loop, 0 for the standalone GEMV hook
+};
+
+// =============================================================================================
+// K1, variant 2 ("tma ring"): the whole A stream goes through TMA bulk copies.
+//
+// One CTA per SM, persistent over a balanced contiguous range of rows.  A producer warp keeps a
+// STAGES-deep shared-memory ring full: one stage = RB row segments of CB columns (RB bulk copies
+// of CB*8 bytes, L2 evict-first: A is read once per iteration and is far larger than L2) plus the
+// matching CB-column slice of p (one bulk copy, L2 evict-last: p is re-read by every CTA).
+// STAGES*RB*CB*8 bytes are in flight per SM regardless of register pressure or occupancy, which
+// is what covers HBM latency at ~50 GB/s per SM.
+// CB/32 consumer warps: thread t owns column t of the stage and all RB rows (RB accumulators), so
+// p is read from shared memory once per RB elements of A and every shared-memory access is a
+// conflict-free 8-byte-per-lane row.  At the end of a pass (RB rows x all columns) the RB
+// accumulators are reduced by warp shuffles, then across warps in fixed order, written to Ap, and
+// p[row]*Ap[row] is added to the CTA's partial of the fused dot product.
+// =============================================================================================
+template <int RB, int CB, int STAGES>
+struct GemvTmaCfg {
+    static constexpr int kConsumerWarps = CB / 32;
+    static constexpr int kThreads = (kConsumerWarps + 1) * 32;
+    static constexpr int kStageDoubles = (RB + 1) * CB;
+    static constexpr size_t kSmemBytes =
+        (size_t)STAGES * kStageDoubles * 8 + 2 * STAGES * 8 + (size_t)kConsumerWarps * RB * 8 + 64;
+};
+
+template <int RB, int CB, int STAGES>
+__global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_tma_kernel(GemvArgs g)
+{
+    using Cfg = GemvTmaCfg<RB, CB, STAGES>;
+    constexpr int NW = Cfg::kConsumerWarps;
+    static_assert(RB <= 32, "final reduction assumes RB <= 32");
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *tiles = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)STAGES * Cfg::kStageDoubles * 8);
+    uint64_t *empty = full + STAGES;
+    double *red = reinterpret_cast<double *>(empty + STAGES); // [NW][RB]
+
+    if (g.check_done && ld_volatile_int(&g.st->done)) return;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const long long base = g.rows / G, rem = g.rows % G;
+    const long long r0 = bid * base + (bid < rem ? bid : rem);
+    const long long rcnt = base + (bid < rem ? 1 : 0);
+    const int npass = (int)((rcnt + RB - 1) / RB);
+    const int nchunk = (int)((g.lda + CB - 1) / CB);
+    const long long total = (long long)npass * nchunk;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (warp == NW) {
+        // ------------------------------------------------------------------ producer
+        if (lane == 0) {
+            const uint64_t polA = l2_policy_evict_first();
+            const uint64_t polP = l2_policy_evict_last();
+            int s = 0;
+            uint32_t ph = 0;
+            int pass = 0, k = 0;
+            for (long long j = 0; j < total; ++j) {
+                if (j >= STAGES) mbar_wait(&empty[s], ph ^ 1u, &g.st->error);
+                const long long prow = r0 + (long long)pass * RB;
+                const long long left = rcnt - (long long)pass * RB;
+                const int nr = left < RB ? (int)left : RB;
+                const long long c0 = (long long)k * CB;
+                const long long cl = g.lda - c0;
+                const uint32_t seg = (uint32_t)((cl < CB ? cl : CB) * 8);
+                double *tile = tiles + (size_t)s * Cfg::kStageDoubles;
+                mbar_arrive_expect_tx(&full[s], seg * (uint32_t)(nr + 1));
+                const double *src = g.A + prow * g.lda + c0;
+                for (int r = 0; r < nr; ++r) tma_load_1d(tile + r * CB, src + (long long)r * g.lda, seg, &full[s], polA);
+                tma_load_1d(tile + RB * CB, g.p + c0, seg, &full[s], polP);
+                if (++k == nchunk) { k = 0; ++pass; }
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    const int col = warp * 32 + lane; // column inside the stage
+    double cta_dot = 0.0;             // meaningful in warp 0 lane 0
+    int s = 0;
+    uint32_t ph = 0;
+    for (int pass = 0; pass < npass; ++pass) {
+        const long long prow = r0 + (long long)pass * RB;
+        const long long left = rcnt - (long long)pass * RB;
+        const int nr = left < RB ? (int)left : RB;
+        double acc[RB];
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = 0.0;
+
+        for (int k = 0; k < nchunk; ++k) {
+            mbar_wait(&full[s], ph, &g.st->error);
+            const double *tile = tiles + (size_t)s * Cfg::kStageDoubles;
+            const long long cl = g.lda - (long long)k * CB;
+            if (col < cl) {
+                const double pv = tile[RB * CB + col];
+                if (nr == RB) {
+#pragma unroll
+                    for (int r = 0; r < RB; ++r) acc[r] = mul_add(tile[r * CB + col], pv, acc[r]);
+                } else {
+#pragma unroll
+                    for (int r = 0; r < RB; ++r)
+                        if (r < nr) acc[r] = mul_add(tile[r * CB + col], pv, acc[r]);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+        }
+
+        // pass epilogue: RB row sums -> Ap, and the fused p.Ap contribution
+#pragma unroll
+        for (int r = 0; r < RB; ++r) acc[r] = warp_sum(acc[r]);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < RB; ++r) red[warp * RB + r] = acc[r];
+        }
+        named_bar_sync(1, NW * 32);
+        if (warp == 0) {
+            double contrib = 0.0;
+            if (lane < nr) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, red[w * RB + lane]);
+                g.Ap[prow + lane] = sum;
+                contrib = __dmul_rn(g.p[g.row_offset + prow + lane], sum);
+            }
+            contrib = warp_sum(contrib);
+            cta_dot = __dadd_rn(cta_dot, contrib);
+        }
+        named_bar_sync(1, NW * 32);
+    }
+
+    if (warp == 0) grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane);
+}
+
+// =============================================================================================
+// K1, variant 1 ("ldg"): A through 128-bit read-only vector loads, p staged in shared memory.
+//
+// 8 warps per CTA, each warp owns R consecutive rows of the current pass and sweeps the columns:
+// one warp-wide load instruction covers 512 contiguous bytes of one row (4 full 128-byte lines,
+// sectors/request = 4), R*U such loads are issued back to back before the first use.  p is staged
+// through a 3-stage shared-memory ring of 2048-column chunks filled by TMA bulk copies (thread 0 is
+// the producer, mbarrier full/empty handshakes), so p costs n*8 bytes of L2 traffic per
+// (8*R)-row pass instead of per row as in the reference kernel (GPU_CUDA.cu:184-191).
+// =============================================================================================
+constexpr int kLdgWarps = 8;
+constexpr int kLdgPChunk = 2048;
+constexpr int kLdgPStages = 3;
+constexpr size_t kLdgSmemBytes = (size_t)kLdgPStages * kLdgPChunk * 8 + 2 * kLdgPStages * 8 + kLdgWarps * 8 + 64;
+
+template <int R, int U>
+__global__ void __launch_bounds__(kLdgWarps * 32, 2) gemv_ldg_kernel(GemvArgs g)
+{
+    constexpr int NW = kLdgWarps, PCH = kLdgPChunk, PST = kLdgPStages;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *pbuf = reinterpret_cast<double *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)PST * PCH * 8);
+    uint64_t *empty = full + PST;
+    double *wdot = reinterpret_cast<double *>(empty + PST);
+
+    if (g.check_done && ld_volatile_int(&g.st->done)) return;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const long long base = g.rows / G, rem = g.rows % G;
+    const long long r0 = bid * base + (bid < rem ? bid : rem);
+    const long long rcnt = base + (bid < rem ? 1 : 0);
+    constexpr int RP = NW * R; // rows per pass
+    const int npass = (int)((rcnt + RP - 1) / RP);
+    const int nchunk = (int)((g.lda + PCH - 1) / PCH);
+    const long long total = (long long)npass * nchunk;
+
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int s = 0; s < PST; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NW);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    const uint64_t polA = l2_policy_evict_first();
+    const uint64_t polP = l2_policy_evict_last();
+    const bool is_producer = (threadIdx.x == 0);
+
+    // producer side: chunk index jj -> stage jj % PST
+    auto issue = [&](long long jj) {
+        const int ss = (int)(jj % PST);
+        const uint32_t pph = (uint32_t)((jj / PST) & 1);
+        if (jj >= PST) mbar_wait(&empty[ss], pph ^ 1u, &g.st->error);
+        const long long c0 = (jj % nchunk) * (long long)PCH;
+        const long long cl = g.lda - c0;
+        const uint32_t bytes = (uint32_t)((cl < PCH ? cl : PCH) * 8);
+        mbar_arrive_expect_tx(&full[ss], bytes);
+        tma_load_1d(pbuf + (size_t)ss * PCH, g.p + c0, bytes, &full[ss], polP);
+    };
+    if (is_producer) {
+        for (long long jj = 0; jj < PST - 1 && jj < total; ++jj) issue(jj);
+    }
+
+    double warp_dot = 0.0;
+    long long j = 0;
+    for (int pass = 0; pass < npass; ++pass) {
+        const long long wrow = r0 + (long long)pass * RP + warp * R; // first row of this warp
+        long long leftw = rcnt - ((long long)pass * RP + warp * R);
+        const int nr = leftw <= 0 ? 0 : (leftw < R ? (int)leftw : R);
+        const double *arow[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) arow[r] = g.A + (wrow + (r < nr ? r : 0)) * g.lda;
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.0;
+
+        for (int k = 0; k < nchunk; ++k, ++j) {
+            if (is_producer && j + PST - 1 < total) issue(j + PST - 1);
+            const int s = (int)(j % PST);
+            const uint32_t ph = (uint32_t)((j / PST) & 1);
+            mbar_wait(&full[s], ph, &g.st->error);
+            const double *pb = pbuf + (size_t)s * PCH;
+            const long long c0 = (long long)k * PCH;
+            const long long cl = g.lda - c0;
+            const int nc = cl < PCH ? (int)cl : PCH; // multiple of 16
+            if (nr > 0) {
+                for (int c = 2 * lane; c < nc; c += 64 * U) {
+                    double2 a[R][U], pv[U];
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int cc = c + 64 * u;
+                        const bool cv = cc < nc;
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            if (cv && r < nr) a[r][u] = ldg_stream_f64x2(arow[r] + c0 + cc, polA);
+                            else a[r][u] = make_double2(0.0, 0.0);
+                        }
+                        pv[u] = cv ? *reinterpret_cast<const double2 *>(pb + cc) : make_double2(0.0, 0.0);
+                    }
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+#pragma unroll
+                        for (int r = 0; r < R; ++r) {
+                            acc[r] = mul_add(a[r][u].x, pv[u].x, acc[r]);
+                            acc[r] = mul_add(a[r][u].y, pv[u].y, acc[r]);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (r < nr) {
+                    g.Ap[wrow + r] = acc[r];
+                    warp_dot = mul_add(g.p[g.row_offset + wrow + r], acc[r], warp_dot);
+                }
+            }
+        }
+    }
+
+    if (lane == 0) wdot[warp] = warp_dot;
+    __syncthreads();
+    if (warp == 0) {
+        double cta_dot = 0.0;
+        if (lane == 0) {
+#pragma unroll
+            for (int w = 0; w < NW; ++w) cta_dot = __dadd_rn(cta_dot, wdot[w]);
+        }
+        grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane);
+    }
+}
+
+// =============================================================================================
+// K2: x += alpha p ; r -= alpha Ap ; partial r.r      (OMP.hpp:71-74; GPU_CUDA.cu:271-279)
+// alpha = rr / (p.Ap) is recomputed by every thread from device-resident scalars.
+// =============================================================================================
+struct VecArgs {
+    DevState *st;
+    const double *pAp_src;  // &st->pAp_local (single rank) or &st->pAp (after all-reduce)
+    const double *rrn_src;  // &st->rrn_local or &st->rrn
+    double *x, *r, *Ap;     // local slices [rows]
+    double *p_full;         // [lda]
+    double *partials;       // [grid]
+    double *hist;           // [hist_cap] sqrt(rr/bb) per iteration (nullable)
+    long long rows, row_offset;
+    int par;                // iteration parity for the double-buffered scalars
+};
+
+__global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
+{
+    __shared__ double scratch[32];
+    DevState *st = v.st;
+    if (ld_volatile_int(&st->done)) return;
+    const double alpha = st->rr[v.par] / *v.pAp_src;
+    const double nalpha = -alpha;
+    const double *p = v.p_full + v.row_offset;
+    double local = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x) {
+        // axpby(alpha, p, 1.0, x) and axpby(-alpha, Ap, 1.0, r): alpha*x[i] + beta*y[i], unfused
+        v.x[i] = __dadd_rn(__dmul_rn(alpha, p[i]), v.x[i]);
+        const double rn = __dadd_rn(__dmul_rn(nalpha, v.Ap[i]), v.r[i]);
+        v.r[i] = rn;
+        local = mul_add(rn, rn, local);
+    }
+    const double cta = block_sum(local, scratch);
+    if (threadIdx.x < 32) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) st->alpha_last = alpha;
+        grid_sum_publish(cta, v.partials, &st->ticket_xr, &st->rrn_local, threadIdx.x);
+    }
+}
+
+// =============================================================================================
+// K3: beta = rr_new / rr ; rr = rr_new ; stop test ; p = r + beta p   (OMP.hpp:75-78)
+// Every thread evaluates the (identical) scalars; thread 0 of CTA 0 commits them to the other
+// parity slot and latches `done`.
+// =============================================================================================
+__global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
+{
+    DevState *st = v.st;
+    if (ld_volatile_int(&st->done)) return;
+    const double rr_old = st->rr[v.par];
+    const double rr_new = *v.rrn_src;
+    const double beta = rr_new / rr_old;
+    const int it = st->iter[v.par] + 1;
+    const double rel = sqrt(rr_new / st->bb);
+    const bool conv = rel < st->eps;
+    const bool fin = conv || it >= st->max_iters;
+
+    if (!conv) { // the reference breaks before the p update only on convergence (OMP.hpp:77-78)
+        double *p = v.p_full + v.row_offset;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x)
+            p[i] = __dadd_rn(v.r[i], __dmul_rn(beta, p[i])); // axpby(1.0, r, beta, p)
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->rr[v.par ^ 1] = rr_new;
+        st->iter[v.par ^ 1] = it;
+        st->iters_done = it;
+        st->rr_final = rr_new;
+        st->beta_last = beta;
+        if (v.hist && it - 1 < st->hist_cap) v.hist[it - 1] = rel;
+        if (fin) {
+            st->converged = conv ? 1 : 0;
+            __threadfence();
+            st->done = 1;
+        }
+    }
+}
+
+// =============================================================================================
+// Solve initialisation (OMP.hpp:56-67): x = 0, r = b_local, p = b, Ap = 0, bb = rr = b.b.
+// One CTA; b.b is summed over the FULL rhs on every rank in the same fixed order, so all ranks
+// hold the same bits without a collective.
+// =============================================================================================
+struct InitArgs {
+    DevState *st;
+    const double *b_full; // [lda] zero padded
+    double *x, *r, *Ap, *p_full;
+    long long n, lda, rows, row_offset;
+    double eps;
+    int max_iters, hist_cap;
+};
+
+__global__ void __launch_bounds__(1024) init_solve_kernel(InitArgs a)
+{
+    __shared__ double scratch[32];
+    double local = 0.0;
+    for (long long i = threadIdx.x; i < a.lda; i += blockDim.x) {
+        const double bi = a.b_full[i];
+        a.p_full[i] = bi;
+        local = mul_add(bi, bi, local);
+    }
+    for (long long i = threadIdx.x; i < a.rows; i += blockDim.x) {
+        a.x[i] = 0.0;
+        a.Ap[i] = 0.0;
+        a.r[i] = a.b_full[a.row_offset + i];
+    }
+    const double bb = block_sum(local, scratch);
+    if (threadIdx.x == 0) {
+        DevState *st = a.st;
+        st->bb = bb;
+        st->rr[0] = bb;
+        st->rr[1] = bb;
+        st->iter[0] = 0;
+        st->iter[1] = 0;
+        st->pAp_local = st->pAp = st->rrn_local = st->rrn = 0.0;
+        st->eps = a.eps;
+        st->rr_final = bb;
+        st->alpha_last = st->beta_last = 0.0;
+        st->max_iters = a.max_iters;
+        st->done = a.max_iters <= 0 ? 1 : 0;
+        st->converged = 0;
+        st->iters_done = 0;
+        st->error = 0;
+        st->hist_cap = a.hist_cap;
+        st->ticket_gemv = st->ticket_xr = st->ticket_misc = 0u;
+    }
+}
+
+// =============================================================================================
+// Generate mode (MPI_OMP.hpp:237-247): local row i is global row g = i + offset;
+// A[i][j] = 2 if g == j, 1 if |g - j| == 1, else 0; pad columns [n, lda) are zero.
+// Written by the GPU straight into the padded HBM layout, two doubles per store.
+// =============================================================================================
+__global__ void __launch_bounds__(256) generate_matrix_kernel(double *A, long long rows, long long n, long long lda, long long offset)
+{
+    const long long half = lda >> 1;
+    const long long total = rows * half;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / half;
+        const long long j = (t - i * half) * 2;
+        const long long gr = i + offset;
+        double2 v;
+        const long long d0 = gr - j, d1 = gr - (j + 1);
+        v.x = (j < n) ? (d0 == 0 ? 2.0 : ((d0 == 1 || d0 == -1) ? 1.0 : 0.0)) : 0.0;
+        v.y = (j + 1 < n) ? (d1 == 0 ? 2.0 : ((d1 == 1 || d1 == -1) ? 1.0 : 0.0)) : 0.0;
+        *reinterpret_cast<double2 *>(A + i * lda + j) = v;
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_kernel(double *v, long long n, long long n_padded, double value)
+{
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (long long)gridDim.x * blockDim.x)
+        v[i] = i < n ? value : 0.0;
+}
+
+// Read-only streaming ceiling: sum of every element of the row block with plain 128-bit loads.
+__global__ void __launch_bounds__(512) stream_read_kernel(const double *A, long long count2, double *partials)
+{
+    __shared__ double scratch[32];
+    const uint64_t pol = l2_policy_evict_first();
+    const double2 *A2 = reinterpret_cast<const double2 *>(A);
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < count2; i += 4 * stride) {
+        const double2 a = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i), pol);
+        const double2 b = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i + stride), pol);
+        const double2 c = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i + 2 * stride), pol);
+        const double2 d = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i + 3 * stride), pol);
+        s0 += a.x + a.y;
+        s1 += b.x + b.y;
+        s2 += c.x + c.y;
+        s3 += d.x + d.y;
+    }
+    for (; i < count2; i += stride) {
+        const double2 a = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i), pol);
+        s0 += a.x + a.y;
+    }
+    const double cta = block_sum((s0 + s1) + (s2 + s3), scratch);
+    if (threadIdx.x == 0) partials[blockIdx.x] = cta;
+}
+
+} // namespace lamcgk

@@ -1,0 +1,145 @@
+/*
+ * lamcg.h — C ABI of the B200-native dense Conjugate-Gradient library (liblamcg.so).
+ *
+ * This is the drop-in boundary for the CG path of edo01/2024-EUMaster4HPC-Student-Challenge.
+ * The reference has no FFI: its boundary is the C++ class LAM::ConjugateGradient<T>
+ * (challenge/main/LAM/src/ConjugateGradient.hpp:9-28) plus the generate-mode extensions of the
+ * distributed classes (LAM/src/CPU/ConjugateGradient_CPU_MPI_OMP.hpp:31-35,
+ * LAM/src/GPU/distributed/ConjugateGradient_MultiGPUS_CUDA_NCCL.cuh:37-41).  Each entry point
+ * below names the reference method it stands behind; the C++ class
+ * LAM::ConjugateGradient_B200<T> (LAM/src/B200/ConjugateGradient_B200.hpp in this repo) and the
+ * Python binding call nothing else.  Plain pointers and sizes only; every function returns
+ * LAMCG_OK (0) or a negative lamcg_status, never throws, never exits.  There is no CPU fallback:
+ * without a CUDA device every call that needs one fails with LAMCG_ERR_CUDA.
+ *
+ * Process model: one lamcg_t per GPU ("rank").  A single-GPU solve uses lamcg_create().  A
+ * multi-GPU solve row-partitions A exactly like the reference (MPI_OMP.hpp:175-196: n/P rows per
+ * rank, remainder to the last) with one rank per process (torchrun / the forking CLI) and either
+ * NCCL collectives (lamcg_comm_init_nccl) or direct NVLink peer stores (lamcg_comm_init_peer).
+ */
+#ifndef LAMCG_H
+#define LAMCG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lamcg lamcg_t;
+
+typedef enum {
+    LAMCG_OK = 0,
+    LAMCG_ERR_INVALID = -1, /* bad argument / call order */
+    LAMCG_ERR_CUDA = -2,    /* CUDA runtime error (message in lamcg_last_error) */
+    LAMCG_ERR_IO = -3,      /* cannot open / short read / short write */
+    LAMCG_ERR_SHAPE = -4,   /* matrix not square, rhs size mismatch, rhs cols != 1 */
+    LAMCG_ERR_NOMEM = -5,   /* device or host allocation failed */
+    LAMCG_ERR_COMM = -6,    /* NCCL / peer-exchange failure */
+    LAMCG_ERR_STATE = -7,   /* e.g. solve before a matrix and rhs exist */
+    LAMCG_ERR_DEVICE = -8   /* a kernel reported a fault (barrier timeout, non-finite scalar) */
+} lamcg_status;
+
+/* What ConjugateGradient::solve reports (OMP.hpp:80-90, MPI_OMP.hpp:122-141). */
+typedef struct {
+    int converged;         /* solve()'s bool: stop test sqrt(rr/bb) < rel_error met within max_iters */
+    int iterations;        /* 1-based index of the stopping iteration; max_iters+1 when not converged
+                              (the reference's loop variable after exit, MPI_OMP.hpp:125) */
+    double rel_residual;   /* sqrt(rr/bb) at exit */
+    double solve_seconds;  /* device time of the iteration loop (CUDA events) */
+    double gemv_seconds;   /* summed device time of the GEMV launches; 0 unless option time_gemv=1 */
+    int iterations_run;    /* iterations actually executed on the device (== min(iterations,max_iters)) */
+    int kernel_launches;   /* kernels of this library launched by this solve (incl. graph nodes) */
+} lamcg_result;
+
+typedef struct {
+    size_t n;           /* global system size (rows == cols) */
+    size_t local_rows;  /* rows of A owned by this rank == ConjugateGradient_*::get_num_rows() */
+    size_t row_offset;  /* first global row owned by this rank */
+    size_t lda;         /* leading dimension (in elements) of the device row block, >= n */
+    int rank, nranks, device, sm_count;
+    int comm_mode;      /* 0 none (single rank), 1 NCCL, 2 peer stores */
+    int has_matrix, has_rhs;
+    int gemv_variant;   /* resolved GEMV kernel: 1 = ldg, 2 = tma ring */
+    int gemv_grid, gemv_block, gemv_smem_bytes;
+} lamcg_info;
+
+/* ---- lifetime ------------------------------------------------------------------------------ */
+/* One rank on CUDA device `device` (ordinal as seen by this process). */
+int lamcg_create(lamcg_t **out, int device);
+/* Rank `rank` of `nranks` of a row-partitioned job (MPI_Comm_rank/size in the reference). */
+int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks);
+void lamcg_destroy(lamcg_t *h);
+/* Last error message of this handle (or of the failed create when h == NULL). */
+const char *lamcg_last_error(const lamcg_t *h);
+const char *lamcg_version(void);
+
+/* ---- options (all optional; also readable from env LAMCG_<KEY>) ----------------------------- */
+/*  gemv_variant  0 auto | 1 ldg | 2 tma ring          loop_mode   0 auto | 1 stream | 2 graph | 3 persistent
+ *  chunk_iters   iterations per graph launch          time_gemv   0/1 event-time every GEMV (stream mode)
+ *  gemv_ctas_per_sm, gemv_stages  tuning overrides     history     0/1 keep sqrt(rr/bb) per iteration (default 1) */
+int lamcg_set_option(lamcg_t *h, const char *key, long long value);
+int lamcg_get_info(const lamcg_t *h, lamcg_info *out);
+
+/* ---- multi-GPU bootstrap -------------------------------------------------------------------- */
+/* NCCL: replaces ncclGetUniqueId + MPI_Bcast(id) + ncclCommInitRank of the reference
+ * (GPU/distributed/ConjugateGradient_MultiGPUS_CUDA_NCCL.cu:320-327).  Rank 0 fills a 128-byte id,
+ * the host program broadcasts it (torch.distributed / shared memory), every rank calls init. */
+#define LAMCG_NCCL_ID_BYTES 128
+int lamcg_comm_nccl_unique_id(void *id_out);
+int lamcg_comm_init_nccl(lamcg_t *h, const void *id);
+/* Peer stores over NVLink (replaces the cudaMemcpyPeerAsync scatter/gather of
+ * GPU/local/ConjugateGradient_MultiGPUS_CUDA.cu:336-376): every rank exports a handle to its
+ * exchange buffer, the host all-gathers the handles, every rank imports all of them. */
+#define LAMCG_PEER_HANDLE_BYTES 128
+int lamcg_comm_peer_export(lamcg_t *h, size_t n, void *handle_out);
+int lamcg_comm_init_peer(lamcg_t *h, const void *all_handles /* nranks * LAMCG_PEER_HANDLE_BYTES */);
+
+/* ---- the system ----------------------------------------------------------------------------- */
+/* generate_matrix(rows, cols) (MPI_OMP.hpp:167-256): this rank's rows of tridiag(1,2,1) stored
+ * dense, written by a device kernel straight into HBM.  rows must equal cols. */
+int lamcg_generate_matrix(lamcg_t *h, size_t rows, size_t cols);
+/* generate_rhs() (MPI_OMP.hpp:144-165): b = 1. */
+int lamcg_generate_rhs(lamcg_t *h);
+/* load_matrix_from_file (OMP.hpp:137-197, MPI_OMP.hpp:307-417): 16-byte header (size_t rows,
+ * size_t cols) + row-major doubles; this rank reads only its own row block, 64-bit sizes. */
+int lamcg_load_matrix(lamcg_t *h, const char *path);
+/* load_rhs_from_file (OMP.hpp:93-135): header cols must be 1 and rows must equal n. */
+int lamcg_load_rhs(lamcg_t *h, const char *path);
+/* In-memory system — the original challenge's solve(A, b, x, size, ...) signature
+ * (test/test_CG_CPU_OMP.cpp:76-79).  A is row-major with leading dimension n and may be a host
+ * or a device pointer.  layout 0: A is the whole n*n matrix (the rank takes its rows);
+ * layout 1: A is only this rank's local_rows*n block. */
+int lamcg_set_matrix(lamcg_t *h, const double *A, size_t n, int layout);
+int lamcg_set_rhs(lamcg_t *h, const double *b, size_t n);
+
+/* ---- solve ---------------------------------------------------------------------------------- */
+/* solve(max_iters, rel_error) (OMP.hpp:49-91): x0 = 0, r = p = b; may be called repeatedly. */
+int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out);
+/* sqrt(rr/bb) after each executed iteration of the last solve; returns the count copied. */
+int lamcg_get_residual_history(lamcg_t *h, double *out, int capacity);
+/* This rank's slice of x (local_rows doubles, host pointer). */
+int lamcg_get_solution_local(lamcg_t *h, double *x_local);
+/* The whole x (n doubles, host pointer); collective over all ranks when nranks > 1. */
+int lamcg_get_solution(lamcg_t *h, double *x);
+/* save_result_to_file (OMP.hpp:199-217): header (n, 1) + x; collective, rank 0 writes.  Unlike
+ * the reference the cols word is a clean 1 (SURVEY §2.4 defect 1) and x, not b, is written
+ * (defect 2). */
+int lamcg_save_solution(lamcg_t *h, const char *path);
+
+/* ---- measurement / test hooks ---------------------------------------------------------------- */
+/* One GEMV of the solver's own kernel on this rank's block: y_local = A_local * p, and the fused
+ * epilogue value sum_i p[row_offset+i]*y_local[i].  Host pointers; p has n entries. */
+int lamcg_gemv(lamcg_t *h, const double *p, double *y_local, double *p_dot_y);
+/* Launch the GEMV kernel `reps` times back to back on the solver's stream and return the average
+ * device milliseconds per launch (CUDA events on that stream), after `warmup` untimed launches. */
+int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch);
+/* Plain streaming read of this rank's block (sum of all elements): the read-only HBM ceiling the
+ * GEMV is compared with.  Returns average ms per pass and the checksum. */
+int lamcg_time_stream_read(lamcg_t *h, int warmup, int reps, double *ms_per_pass, double *checksum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LAMCG_H */

@@ -7,6 +7,12 @@
  * local copy, MPI-IO maps onto stdio.  Only the entry points the reference CPU path calls
  * are provided (ConjugateGradient_CPU_MPI_OMP.hpp:73-74,325-406,464,505 and
  * test_CG_CPU_MPI_OMP.cpp:207-209,289).
+ *
+ * Timing aid: with LAMCG_SHIM_SIZE=P in the environment MPI_Comm_size reports P while this
+ * process stays rank 0, so the reference allocates, generates and multiplies only rank 0's
+ * n/P-row block of the n-column system.  bench.py uses that to time a BOUNDED SAMPLE of a system
+ * too large for a quick CPU run (one rank's share of the work; the numbers it computes are then
+ * not a solution and are never used as an oracle).
  */
 #ifndef LAMCG_ORACLE_MPI_SHIM_H
 #define LAMCG_ORACLE_MPI_SHIM_H
@@ -44,7 +50,14 @@ typedef struct { int unused; } MPI_Status;
 static inline int MPI_Init(int *argc, char ***argv) { (void)argc; (void)argv; return MPI_SUCCESS; }
 static inline int MPI_Finalize(void) { return MPI_SUCCESS; }
 static inline int MPI_Comm_rank(MPI_Comm c, int *rank) { (void)c; *rank = 0; return MPI_SUCCESS; }
-static inline int MPI_Comm_size(MPI_Comm c, int *size) { (void)c; *size = 1; return MPI_SUCCESS; }
+static inline int MPI_Comm_size(MPI_Comm c, int *size)
+{
+    (void)c;
+    const char *e = getenv("LAMCG_SHIM_SIZE");
+    int p = e ? atoi(e) : 1;
+    *size = p > 0 ? p : 1;
+    return MPI_SUCCESS;
+}
 static inline int MPI_Abort(MPI_Comm c, int code) { (void)c; exit(code); return MPI_SUCCESS; }
 static inline int MPI_Barrier(MPI_Comm c) { (void)c; return MPI_SUCCESS; }
 
