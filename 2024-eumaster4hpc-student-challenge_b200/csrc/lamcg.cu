@@ -143,7 +143,7 @@ bool plan_ldg(lamcg *h, GemvPlan &p, int variant)
 int make_plan(lamcg *h)
 {
     int v = (int)h->opt_gemv_variant;
-    if (v == 0) v = 2;
+    if (v == 0) v = 14; // measured on B200 (profiles/r01_gemv_sweep.md): ldg<2,8> is within 1% of the best at every block height
     bool ok = false;
     GemvPlan p;
     switch (v) {
@@ -903,10 +903,10 @@ int lamcg_time_stream_read(lamcg_t *h, int warmup, int reps, double *ms_per_pass
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
     CK(cudaSetDevice(h->device));
     const long long count2 = (long long)(h->local_rows * h->lda / 2);
-    const int grid = std::min(h->sm_count * 4, kMaxGrid);
-    for (int i = 0; i < warmup; ++i) stream_read_kernel<<<grid, 512, 0, h->stream>>>(h->A, count2, h->partials);
+    const int grid = std::min(h->sm_count * 8, kMaxGrid);
+    for (int i = 0; i < warmup; ++i) stream_read_kernel<<<grid, 256, 0, h->stream>>>(h->A, count2, h->partials);
     CK(cudaEventRecord(h->ev_start, h->stream));
-    for (int i = 0; i < reps; ++i) stream_read_kernel<<<grid, 512, 0, h->stream>>>(h->A, count2, h->partials);
+    for (int i = 0; i < reps; ++i) stream_read_kernel<<<grid, 256, 0, h->stream>>>(h->A, count2, h->partials);
     CK(cudaEventRecord(h->ev_stop, h->stream));
     CK(cudaGetLastError());
     std::vector<double> part(grid);

@@ -468,30 +468,32 @@ __global__ void __launch_bounds__(256) fill_kernel(double *v, long long n, long 
         v[i] = i < n ? value : 0.0;
 }
 
-// Read-only streaming ceiling: sum of every element of the row block with plain 128-bit loads.
-__global__ void __launch_bounds__(512) stream_read_kernel(const double *A, long long count2, double *partials)
+// Read-only streaming ceiling: sum of every element of the row block with 128-bit loads.  Each CTA
+// owns one contiguous segment and sweeps it with 8 independent loads per thread in flight — the
+// access pattern of the GEMV minus p, the row structure and the epilogue.
+__global__ void __launch_bounds__(256) stream_read_kernel(const double *A, long long count2, double *partials)
 {
     __shared__ double scratch[32];
     const uint64_t pol = l2_policy_evict_first();
-    const double2 *A2 = reinterpret_cast<const double2 *>(A);
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (; i + 3 * stride < count2; i += 4 * stride) {
-        const double2 a = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i), pol);
-        const double2 b = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i + stride), pol);
-        const double2 c = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i + 2 * stride), pol);
-        const double2 d = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i + 3 * stride), pol);
-        s0 += a.x + a.y;
-        s1 += b.x + b.y;
-        s2 += c.x + c.y;
-        s3 += d.x + d.y;
+    const long long per = (count2 + gridDim.x - 1) / gridDim.x;
+    const long long lo = (long long)blockIdx.x * per;
+    const long long hi = lo + per < count2 ? lo + per : count2;
+    double s[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s[u] = 0.0;
+    long long i = lo + threadIdx.x;
+    for (; i + 7 * 256 < hi; i += 8 * 256) {
+        double2 v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = ldg_stream_f64x2(A + 2 * (i + u * 256), pol);
+#pragma unroll
+        for (int u = 0; u < 8; ++u) s[u] += v[u].x + v[u].y;
     }
-    for (; i < count2; i += stride) {
-        const double2 a = ldg_stream_f64x2(reinterpret_cast<const double *>(A2 + i), pol);
-        s0 += a.x + a.y;
+    for (; i < hi; i += 256) {
+        const double2 v = ldg_stream_f64x2(A + 2 * i, pol);
+        s[0] += v.x + v.y;
     }
-    const double cta = block_sum((s0 + s1) + (s2 + s3), scratch);
+    const double cta = block_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])), scratch);
     if (threadIdx.x == 0) partials[blockIdx.x] = cta;
 }
 
