@@ -75,7 +75,10 @@ def main():
         # normalise the reference's garbage upper header bits so the fixture is stable
         fileformat.write_matrix(px, x)
         o = oracle.cg_solve(A, b, 1000, 1e-9)
+        # the reference's own reduction-order noise: the same unmodified solver, only OMP_NUM_THREADS varies
+        spread = [oracle.ref_omp_solve(A, b, 1000, 1e-9, threads=t).iters for t in range(1, 9)]
         entry = {"n": n, "seed": 42, "iters": int(m.group(1)), "rel_printed": float(m.group(2)),
+                 "iters_by_omp_threads_1_to_8": spread,
                  "cols_word_low32": cols & 0xFFFFFFFF, "oracle_iters": o.iters, "oracle_rel": o.rel,
                  "oracle_bit_identical_x": bool(np.array_equal(x, o.x)), "cond": float(np.linalg.cond(A))}
         gold["file_mode"].append(entry)

@@ -185,7 +185,11 @@ def test_file_mode_golden(solver, golden, golden_dir, n):
     solver.load_rhs(os.path.join(golden_dir, f"spd_n{n}_b.bin"))
     r = solver.solve(1000, 1e-9)
     x_ref = fileformat.read_vector(os.path.join(golden_dir, f"spd_n{n}_x.bin"))
-    assert r.converged and abs(r.iterations - g["iters"]) <= 1
+    # "same iteration count +-1": the unmodified reference itself moves by 2-3 iterations on these systems
+    # when only OMP_NUM_THREADS changes (recorded in the fixture), because the residual hovers around
+    # 1.5e-9 for a dozen iterations before crossing 1e-9; +-1 is applied to that envelope.
+    spread = g["iters_by_omp_threads_1_to_8"]
+    assert r.converged and min(spread) - 1 <= r.iterations <= max(spread) + 1, (r.iterations, spread)
     err = rel_l2(solver.solution(), x_ref)
     REPORT[f"file_golden_x_rel_l2_n{n}"] = err
     REPORT[f"file_golden_iters_n{n}"] = [r.iterations, g["iters"]]
