@@ -14,7 +14,10 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <iostream>
+#include <string>
+#include <vector>
 #include <type_traits>
 
 #include "lamcg.h"
@@ -46,11 +49,6 @@ public:
             h_ = nullptr;
         }
     }
-    // One rank per process of a RankWorld: device = rank, communicator bootstrapped over the world.
-    ConjugateGradient_B200(RankWorld &world, Report report) : ConjugateGradient_B200(world.rank(), world.rank(), world.size(), report)
-    {
-        init_comm(world);
-    }
     ~ConjugateGradient_B200() override { lamcg_destroy(h_); }
     ConjugateGradient_B200(const ConjugateGradient_B200 &) = delete;
     ConjugateGradient_B200 &operator=(const ConjugateGradient_B200 &) = delete;
@@ -60,15 +58,26 @@ public:
     void set_report(Report r) { report_ = r; }
     bool set_option(const char *key, long long v) { return h_ && check(lamcg_set_option(h_, key, v)); }
 
-    // NCCL bootstrap; returns seconds spent (the reference times and prints it, NCCL.cu:306-334).
-    double init_comm(RankWorld &world)
+    // Communicator bootstrap; returns seconds spent (the reference times and prints it, NCCL.cu:306-334).
+    // LAMCG_COMM=peer selects the fused NVLink peer-store exchange (needs the system size n up front
+    // because the exchange buffers are exported before the matrix exists); default is NCCL.
+    double init_comm(RankWorld &world, size_t n = 0)
     {
         if (!h_ || world.size() == 1) return 0.0;
         const auto t0 = std::chrono::steady_clock::now();
-        unsigned char id[LAMCG_NCCL_ID_BYTES] = {0};
-        if (world.rank() == 0 && lamcg_comm_nccl_unique_id(id) != LAMCG_OK) std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
-        world.bcast(id, sizeof id, 0);
-        check(lamcg_comm_init_nccl(h_, id));
+        const char *mode = std::getenv("LAMCG_COMM");
+        if (mode && std::string(mode) == "peer" && n > 0) {
+            unsigned char mine[LAMCG_PEER_HANDLE_BYTES] = {0};
+            std::vector<unsigned char> all((size_t)world.size() * LAMCG_PEER_HANDLE_BYTES);
+            check(lamcg_comm_peer_export(h_, n, mine));
+            world.allgather(mine, sizeof mine, all.data());
+            check(lamcg_comm_init_peer(h_, all.data()));
+        } else {
+            unsigned char id[LAMCG_NCCL_ID_BYTES] = {0};
+            if (world.rank() == 0 && lamcg_comm_nccl_unique_id(id) != LAMCG_OK) std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
+            world.bcast(id, sizeof id, 0);
+            check(lamcg_comm_init_nccl(h_, id));
+        }
         world.barrier();
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }

@@ -23,6 +23,8 @@ import sys
 
 import numpy as np
 
+from . import launch  # noqa: F401  (host-side multi-rank plumbing)
+
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
 LIB_PATH = os.path.join(HERE, "liblamcg.so")

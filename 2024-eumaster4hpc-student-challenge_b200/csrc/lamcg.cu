@@ -70,11 +70,17 @@ struct lamcg {
     // comm
     int comm_mode = kCommNone;
     ncclComm_t nccl = nullptr;
+    // peer exchange (comm_mode == kCommPeer)
+    unsigned char *peer_base = nullptr; // this rank's exchange buffer (cudaMalloc, IPC-exported)
+    size_t peer_bytes = 0, peer_n = 0;
+    PeerView pv{};
+    unsigned long long seq_next = 1, gather_seq = 0;
 
     // graph cache
     cudaGraphExec_t graph_exec = nullptr;
     int graph_chunk = 0;
     int graph_variant = 0;
+    int graph_comm = -1;
     size_t graph_n = 0;
 
     GemvPlan plan;
@@ -110,6 +116,7 @@ struct lamcg {
 namespace {
 
 constexpr int kMaxGrid = 4096;
+using lamcgk::kMaxRanks;
 
 template <int RB, int CB, int ST>
 bool plan_tma(lamcg *h, GemvPlan &p, int variant)
@@ -192,6 +199,8 @@ int alloc_system(lamcg *h, size_t n)
 {
     if (n == 0) return h->fail(LAMCG_ERR_SHAPE, "empty system");
     if (h->alloc_n == n && h->A) return LAMCG_OK;
+    if (h->comm_mode == kCommPeer && n != h->peer_n)
+        return h->fail(LAMCG_ERR_SHAPE, "system size %zu differs from the size %zu the peer exchange buffers were exported for", n, h->peer_n);
     free_system(h);
     CK(cudaSetDevice(h->device));
     h->n = n;
@@ -219,11 +228,26 @@ int alloc_system(lamcg *h, size_t n)
     return LAMCG_OK;
 }
 
-GemvArgs gemv_args(lamcg *h, int check_done)
+double *p_ptr(lamcg *h, int par)
+{
+    if (h->comm_mode == kCommPeer) return reinterpret_cast<double *>(h->peer_base + h->pv.off_p[par & 1]);
+    return h->p_full;
+}
+
+PeerView no_peer()
+{
+    PeerView v{};
+    v.nranks = 0;
+    return v;
+}
+
+GemvArgs gemv_args(lamcg *h, int check_done, int par)
 {
     GemvArgs g;
     g.A = h->A;
-    g.p = h->p_full;
+    g.p = p_ptr(h, par);
+    g.par = par;
+    g.pv = (h->comm_mode == kCommPeer && check_done) ? h->pv : no_peer();
     g.Ap = h->Ap;
     g.partials = h->partials;
     g.st = h->st;
@@ -234,9 +258,9 @@ GemvArgs gemv_args(lamcg *h, int check_done)
     return g;
 }
 
-int launch_gemv(lamcg *h, int check_done)
+int launch_gemv(lamcg *h, int check_done, int par = 0)
 {
-    GemvArgs g = gemv_args(h, check_done);
+    GemvArgs g = gemv_args(h, check_done, par);
     h->plan.kernel<<<h->plan.grid, h->plan.block, h->plan.smem, h->stream>>>(g);
     CK(cudaGetLastError());
     return LAMCG_OK;
@@ -258,7 +282,9 @@ VecArgs vec_args(lamcg *h, int par)
     v.x = h->x;
     v.r = h->r;
     v.Ap = h->Ap;
-    v.p_full = h->p_full;
+    v.p_in = p_ptr(h, par);
+    v.p_out = p_ptr(h, par ^ 1);
+    v.pv = h->comm_mode == kCommPeer ? h->pv : no_peer();
     v.partials = h->partials + kMaxGrid;
     v.hist = h->opt_history ? h->hist : nullptr;
     v.rows = (long long)h->local_rows;
@@ -287,7 +313,7 @@ int enqueue_iteration(lamcg *h, int par, cudaEvent_t ev0, cudaEvent_t ev1, int *
 {
     NcclApi &N = nccl_api();
     if (ev0) CK(cudaEventRecord(ev0, h->stream));
-    int rc = launch_gemv(h, 1);
+    int rc = launch_gemv(h, 1, par);
     if (rc != LAMCG_OK) return rc;
     if (ev1) CK(cudaEventRecord(ev1, h->stream));
     if (h->comm_mode == kCommNccl)
@@ -310,7 +336,7 @@ int enqueue_iteration(lamcg *h, int par, cudaEvent_t ev0, cudaEvent_t ev1, int *
 
 int build_graph(lamcg *h, int chunk)
 {
-    if (h->graph_exec && h->graph_chunk == chunk && h->graph_variant == h->plan.variant && h->graph_n == h->n) return LAMCG_OK;
+    if (h->graph_exec && h->graph_chunk == chunk && h->graph_variant == h->plan.variant && h->graph_n == h->n && h->graph_comm == h->comm_mode) return LAMCG_OK;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
@@ -325,6 +351,7 @@ int build_graph(lamcg *h, int chunk)
     if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
     h->graph_chunk = chunk;
     h->graph_variant = h->plan.variant;
+    h->graph_comm = h->comm_mode;
     h->graph_n = h->n;
     return LAMCG_OK;
 }
@@ -453,6 +480,10 @@ void lamcg_destroy(lamcg_t *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->nccl) nccl_api().CommDestroy(h->nccl);
+    if (h->comm_mode == kCommPeer)
+        for (int r = 0; r < h->nranks; ++r)
+            if (r != h->rank && h->pv.base[r]) cudaIpcCloseMemHandle(h->pv.base[r]);
+    cudaFree(h->peer_base);
     free_system(h);
     for (cudaEvent_t e : h->gemv_events) cudaEventDestroy(e);
     cudaFree(h->hist);
@@ -478,6 +509,7 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "history") h->opt_history = value;
     else if (k == "gemv_ctas_per_sm") h->opt_gemv_ctas_per_sm = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->alloc_n) {
         CK(cudaSetDevice(h->device));
         return make_plan(h);
@@ -539,16 +571,75 @@ int lamcg_comm_init_nccl(lamcg_t *h, const void *id)
     return LAMCG_OK;
 }
 
-int lamcg_comm_peer_export(lamcg_t *h, size_t, void *)
+namespace {
+struct PeerHandleWire { // what travels between ranks: LAMCG_PEER_HANDLE_BYTES
+    cudaIpcMemHandle_t ipc;
+    unsigned long long bytes, n;
+    int rank, pid;
+};
+static_assert(sizeof(PeerHandleWire) <= LAMCG_PEER_HANDLE_BYTES, "peer handle too large");
+} // namespace
+
+int lamcg_comm_peer_export(lamcg_t *h, size_t n, void *handle_out)
 {
-    if (!h) return LAMCG_ERR_INVALID;
-    return h->fail(LAMCG_ERR_INVALID, "peer exchange is not built into this version");
+    if (!h || !handle_out || n == 0) return LAMCG_ERR_INVALID;
+    if (h->nranks > kMaxRanks) return h->fail(LAMCG_ERR_INVALID, "peer exchange supports at most %d ranks", kMaxRanks);
+    if (h->comm_mode != kCommNone) return h->fail(LAMCG_ERR_STATE, "a communicator is already initialised");
+    CK(cudaSetDevice(h->device));
+    if (h->peer_base) { cudaFree(h->peer_base); h->peer_base = nullptr; }
+    const size_t lda = (n + 15) / 16 * 16;
+    const size_t hdr = (sizeof(PeerHeader) + 255) / 256 * 256;
+    h->pv = PeerView{};
+    h->pv.off_p[0] = (long long)hdr;
+    h->pv.off_p[1] = (long long)(hdr + lda * 8);
+    h->pv.off_xg[0] = (long long)(hdr + 2 * lda * 8);
+    h->pv.off_xg[1] = (long long)(hdr + 3 * lda * 8);
+    h->peer_bytes = hdr + 4 * lda * 8;
+    h->peer_n = n;
+    CK(cudaMalloc(&h->peer_base, h->peer_bytes));
+    CK(cudaMemset(h->peer_base, 0, h->peer_bytes));
+    CK(cudaDeviceSynchronize());
+    PeerHandleWire w{};
+    CK(cudaIpcGetMemHandle(&w.ipc, h->peer_base));
+    w.bytes = h->peer_bytes;
+    w.n = n;
+    w.rank = h->rank;
+    w.pid = (int)getpid();
+    memset(handle_out, 0, LAMCG_PEER_HANDLE_BYTES);
+    memcpy(handle_out, &w, sizeof w);
+    return LAMCG_OK;
 }
 
-int lamcg_comm_init_peer(lamcg_t *h, const void *)
+int lamcg_comm_init_peer(lamcg_t *h, const void *all_handles)
 {
-    if (!h) return LAMCG_ERR_INVALID;
-    return h->fail(LAMCG_ERR_INVALID, "peer exchange is not built into this version");
+    if (!h || !all_handles) return LAMCG_ERR_INVALID;
+    if (h->nranks == 1) return LAMCG_OK;
+    if (!h->peer_base) return h->fail(LAMCG_ERR_STATE, "lamcg_comm_peer_export must be called first");
+    CK(cudaSetDevice(h->device));
+    const unsigned char *blob = static_cast<const unsigned char *>(all_handles);
+    for (int r = 0; r < h->nranks; ++r) {
+        PeerHandleWire w;
+        memcpy(&w, blob + (size_t)r * LAMCG_PEER_HANDLE_BYTES, sizeof w);
+        if (w.rank != r || w.n != h->peer_n || w.bytes != h->peer_bytes)
+            return h->fail(LAMCG_ERR_COMM, "peer handle %d is inconsistent (rank %d, n %llu, bytes %llu)", r, w.rank, w.n, w.bytes);
+        if (r == h->rank) {
+            h->pv.base[r] = h->peer_base;
+        } else {
+            void *ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, w.ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                cudaGetLastError();
+                return h->fail(LAMCG_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s (peer access over NVLink is required)", r,
+                               cudaGetErrorString(e));
+            }
+            h->pv.base[r] = static_cast<unsigned char *>(ptr);
+        }
+    }
+    h->pv.me = h->rank;
+    h->pv.nranks = h->nranks;
+    h->comm_mode = kCommPeer;
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    return LAMCG_OK;
 }
 
 // ---- system ---------------------------------------------------------------------------------
@@ -728,7 +819,9 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     ia.x = h->x;
     ia.r = h->r;
     ia.Ap = h->Ap;
-    ia.p_full = h->p_full;
+    ia.p_full = p_ptr(h, 0);
+    ia.seq_base = h->seq_next;
+    h->seq_next += (unsigned long long)std::max(max_iters, 0) + 2ull;
     ia.n = (long long)h->n;
     ia.lda = (long long)h->lda;
     ia.rows = (long long)h->local_rows;
@@ -829,6 +922,19 @@ int lamcg_get_solution(lamcg_t *h, double *x)
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no system");
     if (h->nranks == 1) return lamcg_get_solution_local(h, x);
     CK(cudaSetDevice(h->device));
+    if (h->comm_mode == kCommPeer) {
+        const unsigned long long gseq = ++h->gather_seq;
+        const int buf = (int)(gseq & 1ull);
+        peer_gather_put_kernel<<<vec_grid(h), kVecThreads, 0, h->stream>>>(h->pv, h->x, (long long)h->local_rows, (long long)h->row_offset,
+                                                                          buf, gseq, h->st);
+        CK(cudaGetLastError());
+        peer_gather_wait_kernel<<<1, 32, 0, h->stream>>>(h->pv, gseq, h->st);
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(x, h->peer_base + h->pv.off_xg[buf], h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        cudaError_t se = cudaStreamSynchronize(h->stream);
+        if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "solution gather faulted on the device: %s", cudaGetErrorString(se));
+        return LAMCG_OK;
+    }
     if (h->comm_mode != kCommNccl) return h->fail(LAMCG_ERR_STATE, "get_solution over ranks needs an initialised communicator");
     if (h->local_rows)
         CK(cudaMemcpyAsync(h->x_full + h->row_offset, h->x, h->local_rows * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
@@ -862,8 +968,8 @@ int lamcg_gemv(lamcg_t *h, const double *p, double *y_local, double *p_dot_y)
     if (!h || !p || !y_local) return LAMCG_ERR_INVALID;
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemsetAsync(h->p_full, 0, h->lda * sizeof(double), h->stream));
-    CK(cudaMemcpyAsync(h->p_full, p, h->n * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaMemsetAsync(p_ptr(h, 0), 0, h->lda * sizeof(double), h->stream));
+    CK(cudaMemcpyAsync(p_ptr(h, 0), p, h->n * sizeof(double), cudaMemcpyDefault, h->stream));
     int rc = launch_gemv(h, 0);
     if (rc != LAMCG_OK) return rc;
     if (h->local_rows) CK(cudaMemcpyAsync(y_local, h->Ap, h->local_rows * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

@@ -35,7 +35,74 @@ struct DevState {
     unsigned int ticket_gemv;
     unsigned int ticket_xr;
     unsigned int ticket_misc;
+    unsigned long long seq_base; // peer mode: flags published by this solve are seq_base + iteration index
 };
+
+// ---------------------------------------------------------------------------------------------
+// Peer exchange ("comm_mode peer"): every rank owns one exchange buffer in its HBM, mapped into all
+// other ranks' address spaces (CUDA IPC over NVLink/NVSwitch).  A producer kernel stores its data
+// straight into every consumer's buffer, fences at system scope and then raises a sequence-numbered
+// flag there; the consumer kernel spins on flags in its OWN memory.  That replaces the three
+// collectives of an iteration (all-gather of p, two scalar all-reduces) by stores fused into K1/K2/K3.
+// Scalars are exchanged as all-gather-of-partials + identical fixed-order local sum, so every rank
+// computes bit-identical alpha/beta and trips the `done` latch on the same iteration.
+// ---------------------------------------------------------------------------------------------
+constexpr int kMaxRanks = 16;
+
+struct PeerHeader {
+    unsigned long long p_flag[kMaxRanks];    // [src] = seq: src's slice of p for iteration index (seq - seq_base) has landed
+    unsigned long long pap_flag[kMaxRanks];  // [src] = seq: src's partial of p.Ap for that iteration has landed
+    unsigned long long rrn_flag[kMaxRanks];
+    unsigned long long gather_flag[kMaxRanks];
+    double pap_slot[2][kMaxRanks];           // [iteration parity][src]
+    double rrn_slot[2][kMaxRanks];
+};
+
+struct PeerView {
+    unsigned char *base[kMaxRanks]; // exchange buffer of every rank as mapped in THIS process
+    long long off_p[2];             // byte offsets of the two full-length p buffers
+    long long off_xg[2];            // byte offsets of the two solution-gather buffers
+    int me, nranks;
+};
+
+__device__ __forceinline__ PeerHeader *peer_hdr(const PeerView &pv, int r) { return reinterpret_cast<PeerHeader *>(pv.base[r]); }
+__device__ __forceinline__ double *peer_p(const PeerView &pv, int r, int buf) { return reinterpret_cast<double *>(pv.base[r] + pv.off_p[buf]); }
+__device__ __forceinline__ double *peer_xg(const PeerView &pv, int r, int buf) { return reinterpret_cast<double *>(pv.base[r] + pv.off_xg[buf]); }
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double *p)
+{
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Spin (bounded: ~30 s, then fault instead of hanging the GPU) until all nranks flags reach `seq`.
+// Called by every thread of a CTA; lanes 0..nranks-1 poll, the CTA barrier releases everybody.
+__device__ __forceinline__ void peer_wait_all(const unsigned long long *flags, int nranks, unsigned long long seq, int *err_flag)
+{
+    if ((int)threadIdx.x < nranks) {
+        const long long t0 = clock64();
+        while (ld_acquire_sys_u64(&flags[threadIdx.x]) < seq) {
+            if (clock64() - t0 > 60000000000LL) {
+                *err_flag = 2;
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -154,9 +221,12 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /* >= 32 d
 }
 
 // "Last CTA finishes": every CTA stores its partial, the CTA that draws the last ticket adds the
-// partials in index order and publishes the total.  Called by ONE full warp per CTA.
+// partials in index order and publishes the total — locally, and in peer mode into slot
+// [par][me] of every rank's exchange buffer followed by a release of flag[me] = seq there.
+// Called by ONE full warp per CTA.  which: 0 = p.Ap (K1), 1 = r.r (K2).
 __device__ __forceinline__ void grid_sum_publish(double cta_partial, double *partials, unsigned int *ticket,
-                                                 double *total_out, int lane)
+                                                 double *total_out, int lane, const PeerView *pv = nullptr, int which = 0,
+                                                 int par = 0, unsigned long long seq = 0)
 {
     const int G = gridDim.x, bid = blockIdx.x;
     int last = 0;
@@ -175,7 +245,24 @@ __device__ __forceinline__ void grid_sum_publish(double cta_partial, double *par
             *total_out = s;
             *ticket = 0u;
         }
+        if (pv && pv->nranks > 1 && lane < pv->nranks) {
+            PeerHeader *dst = peer_hdr(*pv, lane);
+            double *slot = which == 0 ? &dst->pap_slot[par][pv->me] : &dst->rrn_slot[par][pv->me];
+            unsigned long long *flag = which == 0 ? &dst->pap_flag[pv->me] : &dst->rrn_flag[pv->me];
+            *reinterpret_cast<volatile double *>(slot) = s;
+            __threadfence_system();
+            st_release_sys_u64(flag, seq);
+        }
     }
+}
+
+// Sum of the nranks partials sitting in this rank's own exchange buffer, in rank order (identical on
+// every rank).  Call after peer_wait_all on the matching flags.
+__device__ __forceinline__ double peer_sum_slots(const double *slots, int nranks)
+{
+    double s = 0.0;
+    for (int r = 0; r < nranks; ++r) s = __dadd_rn(s, ld_relaxed_sys_f64(&slots[r]));
+    return s;
 }
 
 } // namespace lamcgk

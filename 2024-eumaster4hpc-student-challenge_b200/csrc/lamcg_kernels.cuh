@@ -27,7 +27,21 @@ struct GemvArgs {
     long long lda;      // padded columns
     long long row_offset; // global index of local row 0 (p is indexed globally)
     int check_done;     // 1 inside the solve loop, 0 for the standalone GEMV hook
+    int par;            // iteration parity (scalar double-buffer slot, peer slot / p buffer)
+    PeerView pv;        // pv.nranks <= 1: no peer exchange
 };
+
+// Peer mode prologue of K1: p for iteration `it` is complete once every rank's K3 of iteration it-1
+// has raised p_flag (the first iteration reads the locally initialised p = b).  Returns the sequence
+// number this iteration publishes its scalars with.  Called by all threads of the CTA.
+__device__ __forceinline__ unsigned long long gemv_peer_prologue(const GemvArgs &g)
+{
+    if (g.pv.nranks <= 1 || !g.check_done) return 0ull;
+    const int it = g.st->iter[g.par];
+    const unsigned long long base = g.st->seq_base;
+    if (it >= 1) peer_wait_all(peer_hdr(g.pv, g.pv.me)->p_flag, g.pv.nranks, base + (unsigned long long)it, &g.st->error);
+    return base + (unsigned long long)it + 1ull;
+}
 
 // =============================================================================================
 // K1, variant 2 ("tma ring"): the whole A stream goes through TMA bulk copies.
@@ -86,6 +100,7 @@ __global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_
         fence_mbar_init();
     }
     __syncthreads();
+    const unsigned long long seq = gemv_peer_prologue(g);
 
     if (warp == NW) {
         // ------------------------------------------------------------------ producer
@@ -171,7 +186,7 @@ __global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_
         named_bar_sync(1, NW * 32);
     }
 
-    if (warp == 0) grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane);
+    if (warp == 0) grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane, &g.pv, 0, g.par, seq);
 }
 
 // =============================================================================================
@@ -220,6 +235,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) gemv_ldg_kernel(GemvArgs g)
         fence_mbar_init();
     }
     __syncthreads();
+    const unsigned long long seq = gemv_peer_prologue(g);
 
     const uint64_t polA = l2_policy_evict_first();
     const uint64_t polP = l2_policy_evict_last();
@@ -311,7 +327,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) gemv_ldg_kernel(GemvArgs g)
 #pragma unroll
             for (int w = 0; w < NW; ++w) cta_dot = __dadd_rn(cta_dot, wdot[w]);
         }
-        grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane);
+        grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane, &g.pv, 0, g.par, seq);
     }
 }
 
@@ -321,24 +337,39 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) gemv_ldg_kernel(GemvArgs g)
 // =============================================================================================
 struct VecArgs {
     DevState *st;
-    const double *pAp_src;  // &st->pAp_local (single rank) or &st->pAp (after all-reduce)
+    const double *pAp_src;  // &st->pAp_local (single rank) or &st->pAp (after the NCCL all-reduce)
     const double *rrn_src;  // &st->rrn_local or &st->rrn
     double *x, *r, *Ap;     // local slices [rows]
-    double *p_full;         // [lda]
+    const double *p_in;     // [lda] full p of this iteration
+    double *p_out;          // [lda] full p of the next iteration (== p_in except in peer mode)
     double *partials;       // [grid]
     double *hist;           // [hist_cap] sqrt(rr/bb) per iteration (nullable)
     long long rows, row_offset;
     int par;                // iteration parity for the double-buffered scalars
+    PeerView pv;            // pv.nranks <= 1: no peer exchange
 };
 
 __global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
 {
     __shared__ double scratch[32];
+    __shared__ double s_pAp;
     DevState *st = v.st;
     if (ld_volatile_int(&st->done)) return;
-    const double alpha = st->rr[v.par] / *v.pAp_src;
+    unsigned long long seq = 0ull;
+    double pAp;
+    if (v.pv.nranks > 1) { // peer mode: the all-reduce of p.Ap is a wait on nranks flags + a fixed-order sum
+        seq = st->seq_base + (unsigned long long)st->iter[v.par] + 1ull;
+        PeerHeader *me = peer_hdr(v.pv, v.pv.me);
+        peer_wait_all(me->pap_flag, v.pv.nranks, seq, &st->error);
+        if (threadIdx.x == 0) s_pAp = peer_sum_slots(me->pap_slot[v.par], v.pv.nranks);
+        __syncthreads();
+        pAp = s_pAp;
+    } else {
+        pAp = *v.pAp_src;
+    }
+    const double alpha = st->rr[v.par] / pAp;
     const double nalpha = -alpha;
-    const double *p = v.p_full + v.row_offset;
+    const double *p = v.p_in + v.row_offset;
     double local = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x) {
         // axpby(alpha, p, 1.0, x) and axpby(-alpha, Ap, 1.0, r): alpha*x[i] + beta*y[i], unfused
@@ -350,31 +381,70 @@ __global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
     const double cta = block_sum(local, scratch);
     if (threadIdx.x < 32) {
         if (blockIdx.x == 0 && threadIdx.x == 0) st->alpha_last = alpha;
-        grid_sum_publish(cta, v.partials, &st->ticket_xr, &st->rrn_local, threadIdx.x);
+        grid_sum_publish(cta, v.partials, &st->ticket_xr, &st->rrn_local, threadIdx.x, &v.pv, 1, v.par, seq);
     }
 }
 
 // =============================================================================================
 // K3: beta = rr_new / rr ; rr = rr_new ; stop test ; p = r + beta p   (OMP.hpp:75-78)
 // Every thread evaluates the (identical) scalars; thread 0 of CTA 0 commits them to the other
-// parity slot and latches `done`.
+// parity slot and latches `done`.  In peer mode the new p slice is stored straight into every
+// rank's next-iteration p buffer over NVLink (this IS the all-gather), and the last CTA raises
+// p_flag on every rank once all stores are fenced.
+// The p update is skipped on the final iteration (converged — as in the reference, which breaks
+// before it — or max_iters reached, where nobody reads p again).
 // =============================================================================================
 __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
 {
+    __shared__ double s_rrn;
+    __shared__ int s_last;
     DevState *st = v.st;
     if (ld_volatile_int(&st->done)) return;
+    const int it0 = st->iter[v.par];
+    double rr_new;
+    if (v.pv.nranks > 1) {
+        const unsigned long long seq = st->seq_base + (unsigned long long)it0 + 1ull;
+        PeerHeader *me = peer_hdr(v.pv, v.pv.me);
+        peer_wait_all(me->rrn_flag, v.pv.nranks, seq, &st->error);
+        if (threadIdx.x == 0) s_rrn = peer_sum_slots(me->rrn_slot[v.par], v.pv.nranks);
+        __syncthreads();
+        rr_new = s_rrn;
+    } else {
+        rr_new = *v.rrn_src;
+    }
     const double rr_old = st->rr[v.par];
-    const double rr_new = *v.rrn_src;
     const double beta = rr_new / rr_old;
-    const int it = st->iter[v.par] + 1;
+    const int it = it0 + 1;
     const double rel = sqrt(rr_new / st->bb);
     const bool conv = rel < st->eps;
     const bool fin = conv || it >= st->max_iters;
 
-    if (!conv) { // the reference breaks before the p update only on convergence (OMP.hpp:77-78)
-        double *p = v.p_full + v.row_offset;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x)
-            p[i] = __dadd_rn(v.r[i], __dmul_rn(beta, p[i])); // axpby(1.0, r, beta, p)
+    if (!fin) {
+        const double *p = v.p_in + v.row_offset;
+        if (v.pv.nranks > 1) {
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x) {
+                const double pn = __dadd_rn(v.r[i], __dmul_rn(beta, p[i]));
+                for (int q = 0; q < v.pv.nranks; ++q) peer_p(v.pv, q, v.par ^ 1)[v.row_offset + i] = pn;
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                s_last = (atomicAdd(&st->ticket_misc, 1u) == gridDim.x - 1);
+            }
+            __syncthreads();
+            if (s_last) {
+                if (threadIdx.x == 0) st->ticket_misc = 0u;
+                if ((int)threadIdx.x < v.pv.nranks) {
+                    __threadfence_system();
+                    st_release_sys_u64(&peer_hdr(v.pv, threadIdx.x)->p_flag[v.pv.me], st->seq_base + (unsigned long long)it);
+                }
+            }
+        } else {
+            double *po = v.p_out + v.row_offset;
+            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x)
+                po[i] = __dadd_rn(v.r[i], __dmul_rn(beta, p[i])); // axpby(1.0, r, beta, p)
+        }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->rr[v.par ^ 1] = rr_new;
@@ -391,6 +461,38 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
     }
 }
 
+// Solution gather in peer mode (lamcg_get_solution): every rank stores its x slice into buffer
+// `buf` of every rank's exchange area, then raises gather_flag; the wait kernel blocks the stream
+// until all slices have landed locally.
+__global__ void __launch_bounds__(256) peer_gather_put_kernel(PeerView pv, const double *x, long long rows, long long row_offset,
+                                                               int buf, unsigned long long gseq, DevState *st)
+{
+    __shared__ int s_last;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
+        const double xi = x[i];
+        for (int q = 0; q < pv.nranks; ++q) peer_xg(pv, q, buf)[row_offset + i] = xi;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        s_last = (atomicAdd(&st->ticket_misc, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (s_last) {
+        if (threadIdx.x == 0) st->ticket_misc = 0u;
+        if ((int)threadIdx.x < pv.nranks) {
+            __threadfence_system();
+            st_release_sys_u64(&peer_hdr(pv, threadIdx.x)->gather_flag[pv.me], gseq);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(32) peer_gather_wait_kernel(PeerView pv, unsigned long long gseq, DevState *st)
+{
+    peer_wait_all(peer_hdr(pv, pv.me)->gather_flag, pv.nranks, gseq, &st->error);
+}
+
 // =============================================================================================
 // Solve initialisation (OMP.hpp:56-67): x = 0, r = b_local, p = b, Ap = 0, bb = rr = b.b.
 // One CTA; b.b is summed over the FULL rhs on every rank in the same fixed order, so all ranks
@@ -402,6 +504,7 @@ struct InitArgs {
     double *x, *r, *Ap, *p_full;
     long long n, lda, rows, row_offset;
     double eps;
+    unsigned long long seq_base;
     int max_iters, hist_cap;
 };
 
@@ -438,6 +541,7 @@ __global__ void __launch_bounds__(1024) init_solve_kernel(InitArgs a)
         st->error = 0;
         st->hist_cap = a.hist_cap;
         st->ticket_gemv = st->ticket_xr = st->ticket_misc = 0u;
+        st->seq_base = a.seq_base;
     }
 }
 

@@ -54,7 +54,15 @@ int run(LAM::RankWorld &world, const Args &a)
 
     LAM::ConjugateGradient_B200<double> cg(world.rank(), world.rank(), world.size(), LAM::Report::Csv);
     if (!cg.ok()) return 1;
-    const double comm_s = cg.init_comm(world);
+    size_t n_hint = a.n;
+    if (!a.generate) { // file mode: the system size is the first header word (size_t rows)
+        if (FILE *f = std::fopen(a.matrix, "rb")) {
+            unsigned long long hdr[2] = {0, 0};
+            if (std::fread(hdr, sizeof hdr, 1, f) == 1) n_hint = (size_t)hdr[0];
+            std::fclose(f);
+        }
+    }
+    const double comm_s = cg.init_comm(world, n_hint);
     if (root && a.verbose) {
         std::printf("Command line arguments:\n");
         if (a.generate) std::printf("  rows:    %zu\n  cols:    %zu\n  size of the problem: %f GB\n", a.n, a.n, a.n * (double)a.n * 8 / 1024.0 / 1024.0 / 1024.0);

@@ -183,10 +183,7 @@ def run_b200_arm(args):
 
     n, iters = args.n, args.iters
     s = lamcg_b200.Solver(local_rank, rank, world)
-    if world > 1:
-        ids = [lamcg_b200.Solver.nccl_unique_id() if rank == 0 else None]
-        dist.broadcast_object_list(ids, src=0)
-        s.comm_init_nccl(ids[0])
+    lamcg_b200.launch.bootstrap_comm(s, n=n, mode=args.comm, dist=dist)
     if args.gemv_variant:
         s.set_option("gemv_variant", args.gemv_variant)
     t0 = time.perf_counter()
@@ -311,6 +308,8 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=20, help="CG iterations per step of the CPU reference sample")
     ap.add_argument("--gemv-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--comm", default=os.environ.get("LAMCG_COMM", "nccl"), choices=["nccl", "peer"],
+                    help="multi-GPU exchange: NCCL collectives or fused NVLink peer stores")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

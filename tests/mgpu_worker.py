@@ -1,0 +1,93 @@
+"""Worker run under torchrun by tests/test_gpu_multi.py: one rank per GPU, solves through the C ABI with
+the requested communicator and checks the result against the CPU oracle on rank 0.
+
+usage: torchrun --nproc-per-node P tests/mgpu_worker.py <comm: nccl|peer> <out.json>"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, REPO)
+import lamcg_b200  # noqa: E402
+import oracle  # noqa: E402
+from oracle import fileformat, random_spd  # noqa: E402
+
+
+def rel_l2(a, b):
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def main():
+    comm, out_path = sys.argv[1], sys.argv[2]
+    rank, world, local = lamcg_b200.launch.world_from_env()
+    torch.cuda.set_device(local)
+    dist.init_process_group("gloo")  # messenger only; the data path is NCCL / NVLink inside liblamcg
+    report = {"comm": comm, "world": world, "cases": []}
+    ok = True
+
+    def case(name, n, make_system, max_iters, loop_mode, tol):
+        nonlocal ok
+        s = lamcg_b200.Solver(local, rank, world)
+        lamcg_b200.launch.bootstrap_comm(s, n=n, mode=comm, dist=dist)
+        s.set_option("loop_mode", loop_mode)
+        ref = make_system(s)
+        r = s.solve(max_iters, 1e-9)
+        x = s.solution()                   # collective gather through the library
+        rows, off = lamcg_b200.launch.partition(n, world, rank)
+        assert s.info.local_rows == rows and s.info.row_offset == off
+        assert np.array_equal(s.solution_local(), x[off:off + rows])
+        r2 = s.solve(max_iters, 1e-9)      # repeated solve on the same communicator: same bits
+        x2 = s.solution()
+        entry = {"name": name, "n": n, "iters": r.iterations, "oracle_iters": ref.iters, "rel": r.rel_residual,
+                 "x_err": rel_l2(x, ref.x), "repeat_identical": bool(np.array_equal(x, x2) and r2.iterations == r.iterations),
+                 "it_per_s": r.iterations_run / r.solve_seconds}
+        good = (abs(r.iterations - ref.iters) <= (0 if name.startswith("gen") else 1) and entry["x_err"] <= tol
+                and entry["repeat_identical"])
+        entry["ok"] = bool(good)
+        ok = ok and good
+        report["cases"].append(entry)
+        # every rank must hold the same x
+        xs = [None] * world
+        dist.all_gather_object(xs, x.tobytes())
+        assert all(b == xs[0] for b in xs), "ranks disagree on x"
+        s.close()
+
+    def gen(n, max_iters):
+        def mk(s):
+            s.generate_matrix(n, n)
+            s.generate_rhs()
+            return oracle.cg_solve_generated(n, max_iters, 1e-9)
+        return mk
+
+    def spd(n, seed):
+        A, b = random_spd.random_spd_system(n, seed)
+
+        def mk(s):
+            s.set_matrix(A)          # layout 0: every rank is handed the whole matrix and takes its rows
+            s.set_rhs(b)
+            return oracle.cg_solve(A, b, 1000, 1e-9)
+        return mk
+
+    case("gen_even", 4096, gen(4096, 300), 300, 2, 1e-12)
+    case("gen_remainder", 10007, gen(10007, 200), 200, 1, 1e-12)      # n % P != 0: last rank owns the remainder
+    case("gen_converge", 1000, gen(1000, 10000), 10000, 2, 1e-12)     # done latch trips on all ranks at iteration 500
+    case("gen_tiny", 7, gen(7, 50), 50, 2, 1e-12)                     # fewer rows than CTAs, odd split
+    case("spd_file", 1024, spd(1024, 11), 1000, 2, 1e-10)
+    case("gen_big", 40000, gen(40000, 100), 100, 2, 1e-12)
+
+    if rank == 0:
+        report["ok"] = bool(ok)
+        with open(out_path, "w") as f:
+            json.dump(report, f, indent=1)
+        print(json.dumps(report))
+    dist.barrier()
+    dist.destroy_process_group()
+    sys.exit(0 if ok else 1)
+
+
+if __name__ == "__main__":
+    main()
