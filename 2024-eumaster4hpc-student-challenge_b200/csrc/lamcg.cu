@@ -479,6 +479,9 @@ void lamcg_destroy(lamcg_t *h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    // A CUDA graph that captured NCCL kernels keeps the communicator referenced: ncclCommDestroy
+    // blocks until such graphs are gone, so the executable graph goes first.
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->nccl) nccl_api().CommDestroy(h->nccl);
     if (h->comm_mode == kCommPeer)
         for (int r = 0; r < h->nranks; ++r)

@@ -31,7 +31,7 @@ def test_ranked_solve_matches_oracle(comm, world, tmp_path):
     out = str(tmp_path / "report.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(REPO, "tests", "mgpu_worker.py"), comm, out]
-    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=240)
     assert res.returncode == 0, res.stdout[-3000:] + res.stderr[-3000:]
     rep = json.load(open(out))
     assert rep["ok"], rep
