@@ -158,6 +158,7 @@ int main(int argc, char **argv)
     // (test_CG_CPU_MPI_OMP.cpp:281-291); the README documents file mode with the default paths.
     if (!a.generate) a.load = true;
 
+    setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0); // stdout carries exactly one CSV line; NCCL's banner goes to stderr
     LAM::RankWorld world = LAM::RankWorld::launch(0); // forks before any CUDA call
     int rc = run(world, a);
     if (world.rank() == 0) std::cout << std::endl;

@@ -39,3 +39,27 @@ def test_ranked_solve_matches_oracle(comm, world, tmp_path):
     os.makedirs(dst, exist_ok=True)
     with open(os.path.join(dst, f"mgpu_report_{comm}_{world}.json"), "w") as f:
         json.dump(rep, f, indent=1)
+
+
+@pytest.mark.parametrize("comm", ["nccl", "peer"])
+def test_cpp_driver_forked_ranks(comm, tmp_path):
+    """The getopt driver with LAMCG_NGPUS=2: RankWorld forks one process per GPU (the reference uses
+    srun -n 2), rank 0 prints the CSV line and writes the gathered x."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import math
+    import numpy as np
+    import oracle
+    from oracle import fileformat
+    exe = os.path.join(REPO, "2024-eumaster4hpc-student-challenge_b200", "test", "test_CG_MultiGPUS_CUDA_NCCL.out")
+    sol = str(tmp_path / "sol.bin")
+    env = dict(os.environ, LAMCG_NGPUS="2", LAMCG_COMM=comm)
+    n, it = 10007, 150
+    res = subprocess.run([exe, "-s", str(n), "-i", str(it), "-e", "1e-9", "-o", sol], capture_output=True, text=True, env=env, timeout=200)
+    assert res.returncode == 0, res.stdout + res.stderr
+    f = res.stdout.strip().split(",")
+    assert len(f) == 9 and int(f[0]) == n and int(f[1]) == 2 and int(f[6]) == it + 1
+    o = oracle.cg_solve_generated(n, it, 1e-9)
+    assert math.isclose(float(f[7]), o.rel, rel_tol=2e-5)
+    x = fileformat.read_vector(sol)
+    assert np.linalg.norm(x - o.x) / np.linalg.norm(o.x) <= 1e-12
