@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <iostream>
 #include <string>
 #include <vector>
@@ -59,20 +60,34 @@ public:
     bool set_option(const char *key, long long v) { return h_ && check(lamcg_set_option(h_, key, v)); }
 
     // Communicator bootstrap; returns seconds spent (the reference times and prints it, NCCL.cu:306-334).
-    // LAMCG_COMM=peer selects the fused NVLink peer-store exchange (needs the system size n up front
-    // because the exchange buffers are exported before the matrix exists); default is NCCL.
+    // Default: the fused NVLink peer-store exchange (needs the system size n up front because the
+    // exchange buffers are exported before the matrix exists).  LAMCG_COMM=nccl, n == 0, or any rank
+    // failing to map its peers makes ALL ranks use NCCL collectives instead.
     double init_comm(RankWorld &world, size_t n = 0)
     {
         if (!h_ || world.size() == 1) return 0.0;
         const auto t0 = std::chrono::steady_clock::now();
         const char *mode = std::getenv("LAMCG_COMM");
-        if (mode && std::string(mode) == "peer" && n > 0) {
+        bool peer = n > 0 && !(mode && std::string(mode) == "nccl");
+        if (peer) {
             unsigned char mine[LAMCG_PEER_HANDLE_BYTES] = {0};
             std::vector<unsigned char> all((size_t)world.size() * LAMCG_PEER_HANDLE_BYTES);
-            check(lamcg_comm_peer_export(h_, n, mine));
+            int ok = lamcg_comm_peer_export(h_, n, mine) == LAMCG_OK;
+            if (!ok) std::memset(mine, 0, sizeof mine);
             world.allgather(mine, sizeof mine, all.data());
-            check(lamcg_comm_init_peer(h_, all.data()));
-        } else {
+            if (ok) ok = lamcg_comm_init_peer(h_, all.data()) == LAMCG_OK;
+            std::vector<int> oks(world.size());
+            world.allgather(&ok, sizeof ok, oks.data());
+            for (int o : oks) peer = peer && o;
+            if (!peer) { // start over with a clean handle so no half-mapped peer state survives
+                const lamcg_info i = info();
+                if (rank_ == 0) std::fprintf(stderr, "peer exchange unavailable (%s); using NCCL\n", lamcg_last_error(h_));
+                lamcg_destroy(h_);
+                h_ = nullptr;
+                if (lamcg_create_ranked(&h_, i.device, rank_, nranks_) != LAMCG_OK) return 0.0;
+            }
+        }
+        if (!peer) {
             unsigned char id[LAMCG_NCCL_ID_BYTES] = {0};
             if (world.rank() == 0 && lamcg_comm_nccl_unique_id(id) != LAMCG_OK) std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
             world.bcast(id, sizeof id, 0);

@@ -48,7 +48,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._pump, daemon=True).start()
         except Exception:
@@ -183,7 +183,26 @@ def run_b200_arm(args):
 
     n, iters = args.n, args.iters
     s = lamcg_b200.Solver(local_rank, rank, world)
-    lamcg_b200.launch.bootstrap_comm(s, n=n, mode=args.comm, dist=dist)
+    comm_note = None
+    if world > 1:
+        # default: fused NVLink peer-store exchange; if any rank cannot map its peers (no P2P/IPC on this
+        # box) every rank falls back to the NCCL collectives together (both are GPU paths of this library)
+        mode = args.comm
+        if mode == "peer":
+            ok = 1
+            try:
+                lamcg_b200.launch.bootstrap_comm(s, n=n, mode="peer", dist=dist)
+            except lamcg_b200.LamcgError as e:
+                ok, comm_note = 0, f"peer exchange unavailable ({e.message}); NCCL used"
+            t = torch.tensor([ok], device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            if int(t.item()) == 0:
+                s.close()
+                s = lamcg_b200.Solver(local_rank, rank, world)
+                mode = "nccl"
+                comm_note = comm_note or "peer exchange unavailable on another rank; NCCL used"
+        if mode == "nccl":
+            lamcg_b200.launch.bootstrap_comm(s, n=n, mode="nccl", dist=dist)
     if args.gemv_variant:
         s.set_option("gemv_variant", args.gemv_variant)
     t0 = time.perf_counter()
@@ -265,7 +284,7 @@ def run_b200_arm(args):
                        "n": n, "iters_per_step": iters, "rel_error": 1e-9, "ranks": world,
                        "rows_per_gpu": int(info.local_rows), "gemv_variant": int(info.gemv_variant),
                        "gemv_grid": int(info.gemv_grid), "gemv_block": int(info.gemv_block), "gemv_smem": int(info.gemv_smem_bytes),
-                       "comm": {0: "none", 1: "nccl", 2: "peer"}[int(info.comm_mode)],
+                       "comm": {0: "none", 1: "nccl", 2: "peer"}[int(info.comm_mode)], "comm_note": comm_note,
                        "loop": "stream launches with CUDA events around every GEMV (timed region); CUDA-graph loop reported in graph_iterations_per_s",
                        "l2": f"inputs larger than L2: {bytes_per_gemv / 1e9:.1f} GB streamed per GEMV per GPU vs 126 MB L2, no flush needed",
                        "generate_seconds": gen_s},
@@ -304,11 +323,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=100000)
-    ap.add_argument("--iters", type=int, default=50, help="CG iterations per step (our arm)")
+    ap.add_argument("--iters", type=int, default=100, help="CG iterations per step (our arm)")
     ap.add_argument("--ref-iters", type=int, default=20, help="CG iterations per step of the CPU reference sample")
     ap.add_argument("--gemv-variant", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--comm", default=os.environ.get("LAMCG_COMM", "nccl"), choices=["nccl", "peer"],
+    ap.add_argument("--comm", default=os.environ.get("LAMCG_COMM", "peer"), choices=["nccl", "peer"],
                     help="multi-GPU exchange: NCCL collectives or fused NVLink peer stores")
     args = ap.parse_args()
     if args.impl == "reference":
