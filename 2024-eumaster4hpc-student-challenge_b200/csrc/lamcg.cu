@@ -29,7 +29,9 @@ thread_local std::string g_create_error;
 
 constexpr int kVecThreads = 256;
 constexpr int kCommNone = 0, kCommNccl = 1, kCommPeer = 2;
-constexpr int kLoopAuto = 0, kLoopStream = 1, kLoopGraph = 2;
+constexpr int kLoopAuto = 0, kLoopStream = 1, kLoopGraph = 2, kLoopPersistent = 3;
+constexpr size_t kPersistAutoMaxN = 4096;   // A (<= 134 MB) is L2-resident or nearly so: launch latency dominates
+constexpr size_t kPersistMaxN = 16384;      // p must fit in shared memory next to the task partials
 
 struct GemvPlan {
     int variant = 0;
@@ -75,6 +77,7 @@ struct lamcg {
     size_t peer_bytes = 0, peer_n = 0;
     PeerView pv{};
     unsigned long long seq_next = 1, gather_seq = 0;
+    unsigned long long *persist_barrier = nullptr;
 
     // graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -377,6 +380,64 @@ int check_device_error(lamcg *h, const DevState &s)
     return LAMCG_OK;
 }
 
+// ---- persistent single-kernel loop (loop_mode 3 / auto for small single-rank systems) ------------
+int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *out)
+{
+    if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "the persistent loop is single-rank");
+    if (h->n > kPersistMaxN) return h->fail(LAMCG_ERR_INVALID, "the persistent loop supports n <= %zu", kPersistMaxN);
+    if (!h->persist_barrier) CK(cudaMalloc(&h->persist_barrier, sizeof(unsigned long long)));
+    const int grid = (int)std::min<size_t>((size_t)h->sm_count, h->n);
+    const int rows_max = (int)((h->n + grid - 1) / grid);
+    int segs = 1;
+    while (segs * 2 * rows_max <= kPersistThreads / 32 && (size_t)(segs * 2) * 64 <= h->lda) segs *= 2;
+    const size_t smem = (h->lda + (size_t)rows_max * segs) * sizeof(double);
+    CK(cudaFuncSetAttribute(cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int max_blocks = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, cg_persistent_kernel, kPersistThreads, smem));
+    if (max_blocks < 1) return h->fail(LAMCG_ERR_CUDA, "persistent kernel does not fit on an SM (smem %zu)", smem);
+
+    PersistArgs a;
+    a.A = h->A;
+    a.b = h->b_full;
+    a.x = h->x;
+    a.r = h->r;
+    a.hist = h->opt_history ? h->hist : nullptr;
+    a.partials = h->partials;
+    a.barrier = h->persist_barrier;
+    a.st = h->st;
+    a.n = (long long)h->n;
+    a.lda = (long long)h->lda;
+    a.eps = rel_error;
+    a.max_iters = max_iters;
+    a.hist_cap = h->opt_history ? h->hist_cap : 0;
+    a.segs = segs;
+    CK(cudaMemsetAsync(h->persist_barrier, 0, sizeof(unsigned long long), h->stream));
+    CK(cudaMemsetAsync(h->st, 0, sizeof(DevState), h->stream));
+    CK(cudaEventRecord(h->ev_start, h->stream));
+    void *params[] = {&a};
+    CK(cudaLaunchCooperativeKernel((void *)cg_persistent_kernel, dim3(grid), dim3(kPersistThreads), params, smem, h->stream));
+    CK(cudaEventRecord(h->ev_stop, h->stream));
+    CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "the persistent CG kernel faulted: %s", cudaGetErrorString(se));
+    const DevState &s = h->h_st[2];
+    int rc = check_device_error(h, s);
+    if (rc != LAMCG_OK) return rc;
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
+    h->last_hist_count = h->opt_history ? std::min(s.iters_done, h->hist_cap) : 0;
+    if (out) {
+        out->converged = s.converged;
+        out->iterations = s.converged ? s.iters_done : (max_iters < 0 ? 1 : max_iters + 1);
+        out->rel_residual = std::sqrt(s.rr_final / s.bb);
+        out->solve_seconds = ms * 1e-3;
+        out->gemv_seconds = 0.0;
+        out->iterations_run = s.iters_done;
+        out->kernel_launches = 1;
+    }
+    return LAMCG_OK;
+}
+
 // ---- file helpers ------------------------------------------------------------------------------
 int read_header(lamcg *h, int fd, const char *path, size_t *rows, size_t *cols)
 {
@@ -487,6 +548,7 @@ void lamcg_destroy(lamcg_t *h)
         for (int r = 0; r < h->nranks; ++r)
             if (r != h->rank && h->pv.base[r]) cudaIpcCloseMemHandle(h->pv.base[r]);
     cudaFree(h->peer_base);
+    cudaFree(h->persist_barrier);
     free_system(h);
     for (cudaEvent_t e : h->gemv_events) cudaEventDestroy(e);
     cudaFree(h->hist);
@@ -798,8 +860,13 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     if (rc != LAMCG_OK) return rc;
 
     int loop_mode = (int)h->opt_loop_mode;
-    if (loop_mode == kLoopAuto) loop_mode = h->opt_time_gemv ? kLoopStream : kLoopGraph;
+    if (loop_mode == kLoopAuto) {
+        if (h->opt_time_gemv) loop_mode = kLoopStream;
+        else if (h->nranks == 1 && h->n <= kPersistAutoMaxN) loop_mode = kLoopPersistent;
+        else loop_mode = kLoopGraph;
+    }
     if (h->opt_time_gemv) loop_mode = kLoopStream;
+    if (loop_mode == kLoopPersistent) return solve_persistent(h, max_iters, rel_error, out);
     int chunk = (int)std::max<long long>(2, h->opt_chunk_iters);
     chunk += chunk & 1; // the parity double-buffering needs an even number of iterations per chunk
     if (loop_mode == kLoopGraph) {

@@ -601,4 +601,177 @@ __global__ void __launch_bounds__(256) stream_read_kernel(const double *A, long 
     if (threadIdx.x == 0) partials[blockIdx.x] = cta;
 }
 
+// =============================================================================================
+// Persistent single-kernel CG for the latency-bound regime (BASELINE config 5: n = 2048, A = 33.5 MB
+// lives in the 126 MB L2).  One cooperative launch runs the WHOLE solve: an iteration is two
+// grid-wide barriers instead of three kernel launches, the direction vector p never leaves shared
+// memory (every CTA keeps a full copy and recomputes p = r + beta p redundantly from the r slices the
+// other CTAs publish), and alpha/beta are recomputed by every CTA from the same partials in the same
+// order, so all CTAs take the same branch at the stop test.
+//   per iteration:  [p update in smem] -> GEMV of the CTA's rows (row segments spread over 32 warps)
+//                   -> partial p.Ap -> BARRIER -> alpha; x,r of own rows; publish r; partial r.r
+//                   -> BARRIER -> beta, stop test
+// Same arithmetic as K1/K2/K3 (unfused multiply-add, fixed summation order); same reference loop
+// (OMP.hpp:49-91).
+// =============================================================================================
+struct PersistArgs {
+    const double *A;   // [n][lda]
+    const double *b;   // [lda] zero padded
+    double *x;         // [n] out
+    double *r;         // [n] exchange buffer for the r slices
+    double *hist;      // nullable
+    double *partials;  // [2*grid]
+    unsigned long long *barrier; // zeroed by the host before the launch
+    DevState *st;
+    long long n, lda;
+    double eps;
+    int max_iters, hist_cap;
+    int segs;          // column segments per row (rows*segs tasks are dealt to the warps)
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Sense-free counting barrier: the counter only grows; barrier k completes at (k+1)*grid arrivals.
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long target, int *err_flag)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ull);
+        const long long t0 = clock64();
+        while (ld_acquire_gpu_u64(bar) < target) {
+            if (clock64() - t0 > 4000000000LL) {
+                *err_flag = 3;
+                __threadfence_system();
+                __trap();
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Fixed-order sum of `count` doubles written by other CTAs (read through L2), result in all threads.
+__device__ __forceinline__ double cta_sum_global(const double *v, int count, double *s_bcast)
+{
+    if (threadIdx.x < 32) {
+        double s = 0.0;
+        for (int i = threadIdx.x; i < count; i += 32) s = __dadd_rn(s, __ldcg(&v[i]));
+        s = warp_sum(s);
+        if (threadIdx.x == 0) *s_bcast = s;
+    }
+    __syncthreads();
+    const double out = *s_bcast;
+    __syncthreads();
+    return out;
+}
+
+constexpr int kPersistThreads = 1024;
+
+__global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(PersistArgs a)
+{
+    extern __shared__ __align__(16) double psm[];
+    double *p = psm;                       // [lda]
+    double *part = psm + a.lda;            // [rows_max * segs] task partial sums
+    __shared__ double scratch[32];
+    __shared__ double s_bcast;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kPersistThreads / 32;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const long long base = a.n / G, rem = a.n % G;
+    const long long r0 = bid * base + (bid < rem ? bid : rem);
+    const int rcnt = (int)(base + (bid < rem ? 1 : 0));
+    const int S = a.segs;
+    const long long seglen = ((a.lda + S - 1) / S + 1) & ~1LL; // even, so 16-byte loads stay aligned
+    DevState *st = a.st;
+
+    // ---- init: p = b (every CTA), own x = 0, own r = b, bb = b.b (same order in every CTA)
+    double local = 0.0;
+    for (long long i = tid; i < a.lda; i += kPersistThreads) {
+        const double bi = a.b[i];
+        p[i] = bi;
+        local = mul_add(bi, bi, local);
+    }
+    const double bb_t0 = block_sum(local, scratch);
+    if (tid == 0) s_bcast = bb_t0;
+    __syncthreads();
+    const double bb = s_bcast;
+    __syncthreads();
+    double x_own = 0.0, r_own = 0.0, Ap_own = 0.0;
+    if (tid < rcnt) r_own = a.b[r0 + tid];
+
+    double rr = bb, beta = 0.0;
+    unsigned long long bar_target = 0ull;
+    int it;
+    bool converged = false;
+    for (it = 1; it <= a.max_iters; ++it) {
+        if (it > 1) { // p = r + beta p, full vector, from the r slices published before the last barrier
+            for (long long i = tid; i < a.n; i += kPersistThreads) p[i] = __dadd_rn(__ldcg(&a.r[i]), __dmul_rn(beta, p[i]));
+            __syncthreads();
+        }
+        // ---- GEMV of this CTA's rows: task = (row, column segment), one warp per task
+        for (int task = warp; task < rcnt * S; task += nwarps) {
+            const int row = task / S, seg = task - row * S;
+            const long long c0 = seg * seglen;
+            const long long c1 = c0 + seglen < a.lda ? c0 + seglen : a.lda;
+            const double *arow = a.A + (r0 + row) * a.lda;
+            double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+            for (long long c = c0 + 2 * lane; c < c1; c += 64) {
+                const double2 av = __ldg(reinterpret_cast<const double2 *>(arow + c));
+                const double2 pv = *reinterpret_cast<const double2 *>(p + c);
+                acc0 = mul_add(av.x, pv.x, acc0);
+                acc1 = mul_add(av.y, pv.y, acc1);
+            }
+            const double t = warp_sum(__dadd_rn(acc0, acc1));
+            if (lane == 0) part[task] = t;
+        }
+        __syncthreads();
+        double contrib = 0.0;
+        if (tid < rcnt) {
+            double sum = 0.0;
+            for (int q = 0; q < S; ++q) sum = __dadd_rn(sum, part[tid * S + q]);
+            Ap_own = sum;
+            contrib = __dmul_rn(p[r0 + tid], sum);
+        }
+        const double cta_pap = block_sum(contrib, scratch);
+        if (tid == 0) __stcg(&a.partials[bid], cta_pap);
+        bar_target += (unsigned long long)G;
+        grid_barrier(a.barrier, bar_target, &st->error);
+        const double pAp = cta_sum_global(a.partials, G, &s_bcast);
+        const double alpha = rr / pAp;
+        contrib = 0.0;
+        if (tid < rcnt) {
+            x_own = __dadd_rn(__dmul_rn(alpha, p[r0 + tid]), x_own);
+            r_own = __dadd_rn(__dmul_rn(-alpha, Ap_own), r_own);
+            __stcg(&a.r[r0 + tid], r_own);
+            contrib = __dmul_rn(r_own, r_own);
+        }
+        const double cta_rr = block_sum(contrib, scratch);
+        if (tid == 0) __stcg(&a.partials[G + bid], cta_rr);
+        bar_target += (unsigned long long)G;
+        grid_barrier(a.barrier, bar_target, &st->error);
+        const double rr_new = cta_sum_global(a.partials + G, G, &s_bcast);
+        beta = rr_new / rr;
+        rr = rr_new;
+        const double rel = sqrt(rr / bb);
+        if (bid == 0 && tid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel;
+        if (rel < a.eps) { converged = true; break; }
+    }
+    if (tid < rcnt) a.x[r0 + tid] = x_own;
+    if (bid == 0 && tid == 0) {
+        st->bb = bb;
+        st->rr_final = rr;
+        st->iters_done = converged ? it : (a.max_iters > 0 ? a.max_iters : 0);
+        st->converged = converged ? 1 : 0;
+        st->max_iters = a.max_iters;
+        st->eps = a.eps;
+        st->done = 1;
+    }
+}
+
 } // namespace lamcgk
