@@ -153,7 +153,9 @@ bool plan_ldg(lamcg *h, GemvPlan &p, int variant)
 int make_plan(lamcg *h)
 {
     int v = (int)h->opt_gemv_variant;
-    if (v == 0) v = 14; // measured on B200 (profiles/r01_gemv_sweep.md): ldg<2,8> is within 1% of the best at every block height
+    // measured on B200 (profiles/r01_sweep2.log): ldg<4,4> is the fastest on tall blocks (7216 GB/s at 100000 rows),
+    // ldg<2,8> on short ones (7116 GB/s at 12500 rows, where 32-row passes leave a ragged tail)
+    if (v == 0) v = h->local_rows >= 40000 ? 11 : 14;
     bool ok = false;
     GemvPlan p;
     switch (v) {
@@ -162,6 +164,10 @@ int make_plan(lamcg *h)
     case 12: ok = plan_ldg<2, 4>(h, p, v); break;
     case 13: ok = plan_ldg<8, 2>(h, p, v); break;
     case 14: ok = plan_ldg<2, 8>(h, p, v); break;
+    case 15: ok = plan_ldg<1, 16>(h, p, v); break;
+    case 16: ok = plan_ldg<1, 8>(h, p, v); break;
+    case 17: ok = plan_ldg<4, 8>(h, p, v); break;
+    case 18: ok = plan_ldg<2, 16>(h, p, v); break;
     case 2: ok = plan_tma<16, 256, 6>(h, p, v); break;
     case 21: ok = plan_tma<8, 256, 12>(h, p, v); break;
     case 22: ok = plan_tma<32, 128, 6>(h, p, v); break;
@@ -170,6 +176,8 @@ int make_plan(lamcg *h)
     case 25: ok = plan_tma<8, 512, 6>(h, p, v); break;
     case 26: ok = plan_tma<16, 256, 4>(h, p, v); break;
     case 27: ok = plan_tma<16, 256, 3>(h, p, v); break;
+    case 28: ok = plan_tma<8, 256, 8>(h, p, v); break;
+    case 29: ok = plan_tma<16, 128, 8>(h, p, v); break;
     default: return h->fail(LAMCG_ERR_INVALID, "unknown gemv_variant %d", v);
     }
     if (!ok) return h->fail(LAMCG_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed for gemv variant %d: %s", v,

@@ -103,29 +103,31 @@ __global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_
     const unsigned long long seq = gemv_peer_prologue(g);
 
     if (warp == NW) {
-        // ------------------------------------------------------------------ producer
-        if (lane == 0) {
-            const uint64_t polA = l2_policy_evict_first();
-            const uint64_t polP = l2_policy_evict_last();
-            int s = 0;
-            uint32_t ph = 0;
-            int pass = 0, k = 0;
-            for (long long j = 0; j < total; ++j) {
-                if (j >= STAGES) mbar_wait(&empty[s], ph ^ 1u, &g.st->error);
-                const long long prow = r0 + (long long)pass * RB;
-                const long long left = rcnt - (long long)pass * RB;
-                const int nr = left < RB ? (int)left : RB;
-                const long long c0 = (long long)k * CB;
-                const long long cl = g.lda - c0;
-                const uint32_t seg = (uint32_t)((cl < CB ? cl : CB) * 8);
-                double *tile = tiles + (size_t)s * Cfg::kStageDoubles;
-                mbar_arrive_expect_tx(&full[s], seg * (uint32_t)(nr + 1));
-                const double *src = g.A + prow * g.lda + c0;
-                for (int r = 0; r < nr; ++r) tma_load_1d(tile + r * CB, src + (long long)r * g.lda, seg, &full[s], polA);
-                tma_load_1d(tile + RB * CB, g.p + c0, seg, &full[s], polP);
-                if (++k == nchunk) { k = 0; ++pass; }
-                if (++s == STAGES) { s = 0; ph ^= 1u; }
-            }
+        // ------------------------------------------------------------------ producer warp
+        // A 1-D bulk copy costs the issuing thread ~70-100 cycles (measured, profiles/r01_sweep_n100k_first.log:
+        // single-thread issue capped 1-2 KB copies at 4-5 TB/s), so the RB row copies of a stage are issued
+        // by RB different lanes of this warp in one go; lane 0 arms the barrier first, lane RB % 32 .. fetches p.
+        const uint64_t polA = l2_policy_evict_first();
+        const uint64_t polP = l2_policy_evict_last();
+        int s = 0;
+        uint32_t ph = 0;
+        int pass = 0, k = 0;
+        for (long long j = 0; j < total; ++j) {
+            if (j >= STAGES) mbar_wait(&empty[s], ph ^ 1u, &g.st->error); // all lanes wait: all must see the slot free
+            const long long prow = r0 + (long long)pass * RB;
+            const long long left = rcnt - (long long)pass * RB;
+            const int nr = left < RB ? (int)left : RB;
+            const long long c0 = (long long)k * CB;
+            const long long cl = g.lda - c0;
+            const uint32_t seg = (uint32_t)((cl < CB ? cl : CB) * 8);
+            double *tile = tiles + (size_t)s * Cfg::kStageDoubles;
+            if (lane == 0) mbar_arrive_expect_tx(&full[s], seg * (uint32_t)(nr + 1));
+            __syncwarp();
+            const double *src = g.A + prow * g.lda + c0;
+            for (int r = lane; r < nr; r += 32) tma_load_1d(tile + r * CB, src + (long long)r * g.lda, seg, &full[s], polA);
+            if (lane == (RB & 31)) tma_load_1d(tile + RB * CB, g.p + c0, seg, &full[s], polP);
+            if (++k == nchunk) { k = 0; ++pass; }
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
         return;
     }

@@ -14,7 +14,8 @@ the process is chaotic at the 1e-10 level, for the reference and for us alike.  
   * file mode is held to:  x at matched iteration count within 5e-10 of the oracle (1e-10 is recorded
     in the report whenever it is met, which is the common case), the stopping iteration within
     max(3, 2 %) of the oracle's, and — the criterion that does not depend on rounding luck — our x must
-    be as close to the EXACT solution (LAPACK solve) as the reference's x is, within 20 %.
+    be as close to the EXACT solution (LAPACK solve) as the reference's x is, within a factor 2
+    (both sit at ~2-5e-10 from it; the reference's own threads move that distance by tens of %).
 """
 import math
 
@@ -43,6 +44,6 @@ def reference_self_noise(A, b, k, x_oracle):
 
 
 def as_accurate_as_reference(A, b, x_ours, x_oracle):
-    """(ours_err, oracle_err): distances to the exact solution; ours must not be worse by more than 20 %."""
+    """(ours_err, oracle_err): relative distances to the exact solution."""
     x_true = np.linalg.solve(A, b)
     return rel_l2(x_ours, x_true), rel_l2(x_oracle, x_true)
