@@ -68,6 +68,7 @@ struct lamcg {
     // options
     long long opt_gemv_variant = 0, opt_loop_mode = 0, opt_chunk_iters = 16, opt_time_gemv = 0, opt_history = 1;
     long long opt_gemv_ctas_per_sm = 0;
+    long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
 
     // comm
     int comm_mode = kCommNone;
@@ -77,7 +78,8 @@ struct lamcg {
     size_t peer_bytes = 0, peer_n = 0;
     PeerView pv{};
     unsigned long long seq_next = 1, gather_seq = 0;
-    unsigned long long *persist_barrier = nullptr;
+    unsigned long long *persist_ll = nullptr; // [2][G][G][2] tagged partial words (per-CTA inboxes)
+    int persist_ll_grid = 0;
 
     // graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -393,12 +395,25 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
 {
     if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "the persistent loop is single-rank");
     if (h->n > kPersistMaxN) return h->fail(LAMCG_ERR_INVALID, "the persistent loop supports n <= %zu", kPersistMaxN);
-    if (!h->persist_barrier) CK(cudaMalloc(&h->persist_barrier, sizeof(unsigned long long)));
-    const int grid = (int)std::min<size_t>((size_t)h->sm_count, h->n);
+
+    const int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
+    const size_t ll_words = (size_t)4 * grid * grid;
+    if (!h->persist_ll || h->persist_ll_grid < grid) {
+        cudaFree(h->persist_ll);
+        h->persist_ll = nullptr;
+        CK(cudaMalloc(&h->persist_ll, ll_words * sizeof(unsigned long long)));
+        h->persist_ll_grid = grid;
+    }
     const int rows_max = (int)((h->n + grid - 1) / grid);
     int segs = 1;
     while (segs * 2 * rows_max <= kPersistThreads / 32 && (size_t)(segs * 2) * 64 <= h->lda) segs *= 2;
-    const size_t smem = (h->lda + (size_t)rows_max * segs) * sizeof(double);
+    const size_t fixed = (h->lda + (((size_t)rows_max * segs + 1) & ~(size_t)1)) * sizeof(double);
+    int dev_smem_max = 0;
+    CK(cudaDeviceGetAttribute(&dev_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
+    const size_t budget = (size_t)dev_smem_max > fixed + 4096 ? (size_t)dev_smem_max - fixed - 4096 : 0; // 4 KB for static smem
+    int rows_smem = (int)std::min<size_t>((size_t)rows_max, budget / (h->lda * sizeof(double)));
+    if (h->opt_persist_rows_smem >= 0) rows_smem = std::min(rows_smem, (int)h->opt_persist_rows_smem);
+    const size_t smem = fixed + (size_t)rows_smem * h->lda * sizeof(double);
     CK(cudaFuncSetAttribute(cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int max_blocks = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, cg_persistent_kernel, kPersistThreads, smem));
@@ -410,8 +425,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     a.x = h->x;
     a.r = h->r;
     a.hist = h->opt_history ? h->hist : nullptr;
-    a.partials = h->partials;
-    a.barrier = h->persist_barrier;
+    a.ll = h->persist_ll;
     a.st = h->st;
     a.n = (long long)h->n;
     a.lda = (long long)h->lda;
@@ -419,7 +433,9 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     a.max_iters = max_iters;
     a.hist_cap = h->opt_history ? h->hist_cap : 0;
     a.segs = segs;
-    CK(cudaMemsetAsync(h->persist_barrier, 0, sizeof(unsigned long long), h->stream));
+    a.rows_smem = rows_smem;
+    a.rows_max = rows_max;
+    CK(cudaMemsetAsync(h->persist_ll, 0, ll_words * sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->st, 0, sizeof(DevState), h->stream));
     CK(cudaEventRecord(h->ev_start, h->stream));
     void *params[] = {&a};
@@ -537,6 +553,7 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_time_gemv = env_ll("time_gemv", 0);
     h->opt_history = env_ll("history", 1);
     h->opt_gemv_ctas_per_sm = env_ll("gemv_ctas_per_sm", 0);
+    h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
     *out = h;
     return LAMCG_OK;
 }
@@ -556,7 +573,7 @@ void lamcg_destroy(lamcg_t *h)
         for (int r = 0; r < h->nranks; ++r)
             if (r != h->rank && h->pv.base[r]) cudaIpcCloseMemHandle(h->pv.base[r]);
     cudaFree(h->peer_base);
-    cudaFree(h->persist_barrier);
+    cudaFree(h->persist_ll);
     free_system(h);
     for (cudaEvent_t e : h->gemv_events) cudaEventDestroy(e);
     cudaFree(h->hist);
@@ -581,6 +598,7 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "time_gemv") h->opt_time_gemv = value;
     else if (k == "history") h->opt_history = value;
     else if (k == "gemv_ctas_per_sm") h->opt_gemv_ctas_per_sm = value;
+    else if (k == "persist_rows_smem") h->opt_persist_rows_smem = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->alloc_n) {

@@ -611,8 +611,8 @@ __global__ void __launch_bounds__(256) stream_read_kernel(const double *A, long 
 // other CTAs publish), and alpha/beta are recomputed by every CTA from the same partials in the same
 // order, so all CTAs take the same branch at the stop test.
 //   per iteration:  [p update in smem] -> GEMV of the CTA's rows (row segments spread over 32 warps)
-//                   -> partial p.Ap -> BARRIER -> alpha; x,r of own rows; publish r; partial r.r
-//                   -> BARRIER -> beta, stop test
+//                   -> partial p.Ap -> ALL-GATHER+SUM (flags) -> alpha; x,r of own rows; publish r; partial r.r
+//                   -> ALL-GATHER+SUM (flags) -> beta, stop test
 // Same arithmetic as K1/K2/K3 (unfused multiply-add, fixed summation order); same reference loop
 // (OMP.hpp:49-91).
 // =============================================================================================
@@ -622,13 +622,14 @@ struct PersistArgs {
     double *x;         // [n] out
     double *r;         // [n] exchange buffer for the r slices
     double *hist;      // nullable
-    double *partials;  // [2*grid]
-    unsigned long long *barrier; // zeroed by the host before the launch
+    unsigned long long *ll;      // [2][grid dst][grid src][2] tagged partial words (p.Ap inboxes, then r.r), zeroed by the host
     DevState *st;
     long long n, lda;
     double eps;
     int max_iters, hist_cap;
     int segs;          // column segments per row (rows*segs tasks are dealt to the warps)
+    int rows_smem;     // the first rows_smem rows of every CTA's block stay resident in shared memory
+    int rows_max;      // max rows per CTA (sizes the task-partial array)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
@@ -638,62 +639,111 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
     return v;
 }
 
-// Sense-free counting barrier: the counter only grows; barrier k completes at (k+1)*grid arrivals.
-__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long target, int *err_flag)
+__device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long *p, unsigned long long v)
 {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Grid-wide "all-gather + fixed-order sum" that doubles as the grid barrier, in ONE L2 round trip.
+// Push model: CTA src stores its partial into slot [dst][src] of EVERY CTA's private inbox (thread t
+// serves dst = t), as two 8-byte words {tag:32 | half of the double:32} — the NCCL "LL" idea: an
+// aligned 8-byte store is single-copy atomic, so a word whose tag matches carries valid data and no
+// separate flag or second trip is needed.  Each CTA then polls only its OWN inbox (thread t polls
+// source t), so no cache line is polled by more than one SM (a shared flag array polled by all 148
+// SMs measured 2x slower than a plain atomic-counter barrier).  The G values go through shared memory
+// and are added in index order, so every CTA gets the same bits.  Everything a CTA wrote before the
+// call (its r slice) is visible to all CTAs after it.
+constexpr int kPersistMaxGrid = 256;
+
+// kPublishes: the CTA wrote global data (its r slice) that the other CTAs read after this call, so the
+// stores need a release fence before and the polls an acquire fence after; the p.Ap exchange moves
+// nothing but the tagged words themselves and skips both.
+template <bool kPublishes>
+__device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsigned long long *inbox /* [G dst][G src][2] */,
+                                                     unsigned int tag, double *s_gather /* [kPersistMaxGrid] */, double *s_bcast,
+                                                     int *err_flag)
+{
+    const int G = gridDim.x, t = threadIdx.x;
+    if (t == 0) *s_bcast = my_partial_t0; // block_sum() left the CTA partial in thread 0 only
     __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        atomicAdd(bar, 1ull);
+    if (t < G) {
+        const unsigned long long bits = (unsigned long long)__double_as_longlong(*s_bcast);
+        unsigned long long *dst = inbox + ((size_t)t * G + blockIdx.x) * 2;
+        // release: ONE fence, then relaxed stores (st.release would fence once per word);
+        // acquire: relaxed polling loads, then ONE fence after the loop
+        if (kPublishes) __threadfence();
+        st_relaxed_gpu_u64(dst + 0, ((unsigned long long)tag << 32) | (bits >> 32));
+        st_relaxed_gpu_u64(dst + 1, ((unsigned long long)tag << 32) | (bits & 0xffffffffull));
+        const unsigned long long *src = inbox + ((size_t)blockIdx.x * G + t) * 2;
+        unsigned long long w0, w1;
         const long long t0 = clock64();
-        while (ld_acquire_gpu_u64(bar) < target) {
+        for (;;) {
+            w0 = ld_relaxed_gpu_u64(src + 0);
+            w1 = ld_relaxed_gpu_u64(src + 1);
+            if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag) break;
             if (clock64() - t0 > 4000000000LL) {
                 *err_flag = 3;
                 __threadfence_system();
                 __trap();
             }
         }
+        if (kPublishes) __threadfence();
+        s_gather[t] = __longlong_as_double((long long)(((w0 & 0xffffffffull) << 32) | (w1 & 0xffffffffull)));
     }
     __syncthreads();
-}
-
-// Fixed-order sum of `count` doubles written by other CTAs (read through L2), result in all threads.
-__device__ __forceinline__ double cta_sum_global(const double *v, int count, double *s_bcast)
-{
-    if (threadIdx.x < 32) {
-        double s = 0.0;
-        for (int i = threadIdx.x; i < count; i += 32) s = __dadd_rn(s, __ldcg(&v[i]));
+    // fixed-order sum by warp 0; the result is returned in ALL LANES OF WARP 0 ONLY (0.0 elsewhere): the caller
+    // derives the scalars every thread needs (alpha / beta / stop flag) once, in warp 0, and broadcasts those —
+    // fp64 divisions and the square root executed by all 32 warps cost ~1.3 us of FP64 pipe time per iteration.
+    double s = 0.0;
+    if (t < 32) {
+        for (int i = t; i < G; i += 32) s = __dadd_rn(s, s_gather[i]);
         s = warp_sum(s);
-        if (threadIdx.x == 0) *s_bcast = s;
     }
-    __syncthreads();
-    const double out = *s_bcast;
-    __syncthreads();
-    return out;
+    return s;
 }
 
 constexpr int kPersistThreads = 1024;
 
+// CTA partial of the row owners' contributions (threads 0..rows-1), valid in thread 0.  With at most 32
+// rows per CTA (n <= 32 * grid, the whole latency regime) only warp 0 holds non-zero terms, so one
+// shuffle reduction does it with no shared memory and no CTA barrier; otherwise the general block sum.
+__device__ __forceinline__ double persist_cta_sum(double contrib, bool single_warp, double *scratch)
+{
+    if (single_warp) return threadIdx.x < 32 ? warp_sum(contrib) : 0.0;
+    return block_sum(contrib, scratch);
+}
+
 __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(PersistArgs a)
 {
+    // n <= 16384 in this kernel, so every index fits 32 bits (keeps the 64-register budget spill-free)
     extern __shared__ __align__(16) double psm[];
-    double *p = psm;                       // [lda]
-    double *part = psm + a.lda;            // [rows_max * segs] task partial sums
+    const int n = (int)a.n, lda = (int)a.lda, S = a.segs;
+    double *p = psm;                                  // [lda]
+    double *part = psm + lda;                         // [rows_max * segs] task partial sums
+    double *arows = part + ((a.rows_max * S + 1) & ~1); // [rows_smem][lda] resident rows of A
     __shared__ double scratch[32];
     __shared__ double s_bcast;
+    __shared__ double s_gather[kPersistMaxGrid];
+    __shared__ double s_scal[4]; // alpha | beta | rr | converged, computed once per CTA by thread 0
 
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = kPersistThreads / 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int nwarps = kPersistThreads / 32;
     const int G = gridDim.x, bid = blockIdx.x;
-    const long long base = a.n / G, rem = a.n % G;
-    const long long r0 = bid * base + (bid < rem ? bid : rem);
-    const int rcnt = (int)(base + (bid < rem ? 1 : 0));
-    const int S = a.segs;
-    const long long seglen = ((a.lda + S - 1) / S + 1) & ~1LL; // even, so 16-byte loads stay aligned
+    const int base = n / G, rem = n % G;
+    const int r0 = bid * base + (bid < rem ? bid : rem);
+    const int rcnt = base + (bid < rem ? 1 : 0);
+    const int seglen = ((lda + S - 1) / S + 1) & ~1; // even, so 16-byte loads stay aligned
     DevState *st = a.st;
 
     // ---- init: p = b (every CTA), own x = 0, own r = b, bb = b.b (same order in every CTA)
     double local = 0.0;
-    for (long long i = tid; i < a.lda; i += kPersistThreads) {
+    for (int i = tid; i < lda; i += kPersistThreads) {
         const double bi = a.b[i];
         p[i] = bi;
         local = mul_add(bi, bi, local);
@@ -702,32 +752,50 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
     if (tid == 0) s_bcast = bb_t0;
     __syncthreads();
     const double bb = s_bcast;
-    __syncthreads();
     double x_own = 0.0, r_own = 0.0, Ap_own = 0.0;
     if (tid < rcnt) r_own = a.b[r0 + tid];
+    // A is constant over the solve: park as many of this CTA's rows as fit in shared memory once, so an
+    // iteration re-reads only the remaining rows from L2 (n = 2048: 13 of the 13-14 rows per CTA are resident)
+    const int nres = rcnt < a.rows_smem ? rcnt : a.rows_smem;
+    {
+        const double *src = a.A + (size_t)r0 * lda;
+        for (int i = 2 * tid; i < nres * lda; i += 2 * kPersistThreads)
+            *reinterpret_cast<double2 *>(arows + i) = __ldg(reinterpret_cast<const double2 *>(src + i));
+    }
+    __syncthreads();
 
     double rr = bb, beta = 0.0;
-    unsigned long long bar_target = 0ull;
     int it;
     bool converged = false;
     for (it = 1; it <= a.max_iters; ++it) {
-        if (it > 1) { // p = r + beta p, full vector, from the r slices published before the last barrier
-            for (long long i = tid; i < a.n; i += kPersistThreads) p[i] = __dadd_rn(__ldcg(&a.r[i]), __dmul_rn(beta, p[i]));
+        if (it > 1) { // p = r + beta p, full vector, from the r slices every CTA published before its r.r partial
+            for (int i = tid; i < n; i += kPersistThreads) p[i] = __dadd_rn(__ldcg(&a.r[i]), __dmul_rn(beta, p[i]));
             __syncthreads();
         }
         // ---- GEMV of this CTA's rows: task = (row, column segment), one warp per task
         for (int task = warp; task < rcnt * S; task += nwarps) {
             const int row = task / S, seg = task - row * S;
-            const long long c0 = seg * seglen;
-            const long long c1 = c0 + seglen < a.lda ? c0 + seglen : a.lda;
-            const double *arow = a.A + (r0 + row) * a.lda;
+            const int c0 = seg * seglen;
+            const int c1 = c0 + seglen < lda ? c0 + seglen : lda;
             double acc0 = 0.0, acc1 = 0.0;
+            if (row < nres) {
+                const double *arow = arows + row * lda;
+#pragma unroll 4
+                for (int c = c0 + 2 * lane; c < c1; c += 64) {
+                    const double2 av = *reinterpret_cast<const double2 *>(arow + c);
+                    const double2 pv = *reinterpret_cast<const double2 *>(p + c);
+                    acc0 = mul_add(av.x, pv.x, acc0);
+                    acc1 = mul_add(av.y, pv.y, acc1);
+                }
+            } else {
+                const double *arow = a.A + (size_t)(r0 + row) * lda;
 #pragma unroll 8
-            for (long long c = c0 + 2 * lane; c < c1; c += 64) {
-                const double2 av = __ldg(reinterpret_cast<const double2 *>(arow + c));
-                const double2 pv = *reinterpret_cast<const double2 *>(p + c);
-                acc0 = mul_add(av.x, pv.x, acc0);
-                acc1 = mul_add(av.y, pv.y, acc1);
+                for (int c = c0 + 2 * lane; c < c1; c += 64) {
+                    const double2 av = __ldg(reinterpret_cast<const double2 *>(arow + c));
+                    const double2 pv = *reinterpret_cast<const double2 *>(p + c);
+                    acc0 = mul_add(av.x, pv.x, acc0);
+                    acc1 = mul_add(av.y, pv.y, acc1);
+                }
             }
             const double t = warp_sum(__dadd_rn(acc0, acc1));
             if (lane == 0) part[task] = t;
@@ -740,12 +808,11 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
             Ap_own = sum;
             contrib = __dmul_rn(p[r0 + tid], sum);
         }
-        const double cta_pap = block_sum(contrib, scratch);
-        if (tid == 0) __stcg(&a.partials[bid], cta_pap);
-        bar_target += (unsigned long long)G;
-        grid_barrier(a.barrier, bar_target, &st->error);
-        const double pAp = cta_sum_global(a.partials, G, &s_bcast);
-        const double alpha = rr / pAp;
+        const double cta_pap = persist_cta_sum(contrib, a.rows_max <= 32, scratch);
+        const double pAp_w0 = grid_allgather_sum<false>(cta_pap, a.ll, (unsigned int)it, s_gather, &s_bcast, &st->error);
+        if (tid == 0) s_scal[0] = rr / pAp_w0; // alpha = rr / (p.Ap)
+        __syncthreads();
+        const double alpha = s_scal[0];
         contrib = 0.0;
         if (tid < rcnt) {
             x_own = __dadd_rn(__dmul_rn(alpha, p[r0 + tid]), x_own);
@@ -753,16 +820,19 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
             __stcg(&a.r[r0 + tid], r_own);
             contrib = __dmul_rn(r_own, r_own);
         }
-        const double cta_rr = block_sum(contrib, scratch);
-        if (tid == 0) __stcg(&a.partials[G + bid], cta_rr);
-        bar_target += (unsigned long long)G;
-        grid_barrier(a.barrier, bar_target, &st->error);
-        const double rr_new = cta_sum_global(a.partials + G, G, &s_bcast);
-        beta = rr_new / rr;
-        rr = rr_new;
-        const double rel = sqrt(rr / bb);
-        if (bid == 0 && tid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel;
-        if (rel < a.eps) { converged = true; break; }
+        const double cta_rr = persist_cta_sum(contrib, a.rows_max <= 32, scratch);
+        const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)2 * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
+        if (tid == 0) {
+            const double rel0 = sqrt(rrn_w0 / bb);
+            s_scal[1] = rrn_w0 / rr; // beta = rr_new / rr
+            s_scal[2] = rrn_w0;
+            s_scal[3] = rel0 < a.eps ? 1.0 : 0.0;
+            if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
+        }
+        __syncthreads();
+        beta = s_scal[1];
+        rr = s_scal[2];
+        if (s_scal[3] != 0.0) { converged = true; break; }
     }
     if (tid < rcnt) a.x[r0 + tid] = x_own;
     if (bid == 0 && tid == 0) {

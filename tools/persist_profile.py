@@ -1,0 +1,17 @@
+#!/usr/bin/env python
+"""One persistent-loop solve (for ncu): python tools/persist_profile.py [n] [iters]"""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lamcg_b200  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+iters = int(sys.argv[2]) if len(sys.argv) > 2 else 500
+s = lamcg_b200.Solver(0)
+s.generate_matrix(n, n)
+s.generate_rhs()
+s.set_option("loop_mode", 3)
+r = s.solve(iters, 0.0)
+print(n, iters, r.iterations_run / r.solve_seconds, "it/s")
+s.close()
