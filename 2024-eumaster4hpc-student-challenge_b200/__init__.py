@@ -96,6 +96,7 @@ _SIGNATURES = {
     "lamcg_save_solution": (ctypes.c_int, [_vp, _cp]),
     "lamcg_gemv": (ctypes.c_int, [_vp, _dp, _dp, _dp]),
     "lamcg_time_gemv": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp]),
+    "lamcg_get_loop_profile": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
     "lamcg_time_stream_read": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp, _dp]),
 }
 
@@ -265,6 +266,13 @@ class Solver:
         ms = ctypes.c_double()
         self._ck(self._L.lamcg_time_gemv(self._h, warmup, reps, ctypes.byref(ms)))
         return ms.value
+
+    def loop_profile(self) -> list[int]:
+        """SM cycles per phase of the last persistent-loop solve (CTA 0): p update, GEMV, row sums,
+        p.Ap exchange, x/r update, r.r exchange."""
+        buf = (ctypes.c_longlong * 8)()
+        cnt = self._ck(self._L.lamcg_get_loop_profile(self._h, buf, 8))
+        return [int(buf[i]) for i in range(min(cnt, 6))]
 
     def time_stream_read(self, warmup: int = 2, reps: int = 5) -> tuple[float, float]:
         ms, cs = ctypes.c_double(), ctypes.c_double()

@@ -1099,6 +1099,14 @@ int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch)
     return LAMCG_OK;
 }
 
+int lamcg_get_loop_profile(lamcg_t *h, long long *cycles_out, int capacity)
+{
+    if (!h || !cycles_out || capacity < 0) return LAMCG_ERR_INVALID;
+    const int cnt = std::min(capacity, 8);
+    for (int k = 0; k < cnt; ++k) cycles_out[k] = h->h_st[2].phase_cycles[k];
+    return cnt;
+}
+
 int lamcg_time_stream_read(lamcg_t *h, int warmup, int reps, double *ms_per_pass, double *checksum)
 {
     if (!h || reps <= 0 || !ms_per_pass) return LAMCG_ERR_INVALID;

@@ -36,6 +36,7 @@ struct DevState {
     unsigned int ticket_xr;
     unsigned int ticket_misc;
     unsigned long long seq_base; // peer mode: flags published by this solve are seq_base + iteration index
+    long long phase_cycles[8];   // persistent loop, CTA 0: SM cycles spent per phase (see lamcg_get_loop_profile)
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -767,11 +767,15 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
     double rr = bb, beta = 0.0;
     int it;
     bool converged = false;
+    long long ph[6] = {0, 0, 0, 0, 0, 0}; // phase timers (CTA 0 thread 0 reports): p update, GEMV, row sums, p.Ap exchange, x/r update, r.r exchange
+    long long tc = clock64();
+#define LAMCG_PHASE(k) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; }
     for (it = 1; it <= a.max_iters; ++it) {
         if (it > 1) { // p = r + beta p, full vector, from the r slices every CTA published before its r.r partial
             for (int i = tid; i < n; i += kPersistThreads) p[i] = __dadd_rn(__ldcg(&a.r[i]), __dmul_rn(beta, p[i]));
             __syncthreads();
         }
+        LAMCG_PHASE(0)
         // ---- GEMV of this CTA's rows: task = (row, column segment), one warp per task
         for (int task = warp; task < rcnt * S; task += nwarps) {
             const int row = task / S, seg = task - row * S;
@@ -801,6 +805,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
             if (lane == 0) part[task] = t;
         }
         __syncthreads();
+        LAMCG_PHASE(1)
         double contrib = 0.0;
         if (tid < rcnt) {
             double sum = 0.0;
@@ -809,10 +814,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
             contrib = __dmul_rn(p[r0 + tid], sum);
         }
         const double cta_pap = persist_cta_sum(contrib, a.rows_max <= 32, scratch);
+        LAMCG_PHASE(2)
         const double pAp_w0 = grid_allgather_sum<false>(cta_pap, a.ll, (unsigned int)it, s_gather, &s_bcast, &st->error);
         if (tid == 0) s_scal[0] = rr / pAp_w0; // alpha = rr / (p.Ap)
         __syncthreads();
         const double alpha = s_scal[0];
+        LAMCG_PHASE(3)
         contrib = 0.0;
         if (tid < rcnt) {
             x_own = __dadd_rn(__dmul_rn(alpha, p[r0 + tid]), x_own);
@@ -821,6 +828,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
             contrib = __dmul_rn(r_own, r_own);
         }
         const double cta_rr = persist_cta_sum(contrib, a.rows_max <= 32, scratch);
+        LAMCG_PHASE(4)
         const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)2 * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
         if (tid == 0) {
             const double rel0 = sqrt(rrn_w0 / bb);
@@ -832,6 +840,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
         __syncthreads();
         beta = s_scal[1];
         rr = s_scal[2];
+        LAMCG_PHASE(5)
         if (s_scal[3] != 0.0) { converged = true; break; }
     }
     if (tid < rcnt) a.x[r0 + tid] = x_own;
@@ -843,7 +852,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
         st->max_iters = a.max_iters;
         st->eps = a.eps;
         st->done = 1;
+        for (int k = 0; k < 6; ++k) st->phase_cycles[k] = ph[k];
     }
+#undef LAMCG_PHASE
 }
 
 } // namespace lamcgk
