@@ -2,6 +2,9 @@
 // CUDA-graph driven), multi-GPU plumbing, file ingest, and the extern "C" surface of
 // include/lamcg.h.  No CPU fallback anywhere: every compute entry point needs the GPU.
 #include <algorithm>
+#include <atomic>
+#include <mutex>
+#include <thread>
 #include <cerrno>
 #include <cmath>
 #include <cstdarg>
@@ -68,6 +71,7 @@ struct lamcg {
     // options
     long long opt_gemv_variant = 0, opt_loop_mode = 0, opt_chunk_iters = 16, opt_time_gemv = 0, opt_history = 1;
     long long opt_gemv_ctas_per_sm = 0;
+    long long opt_ingest_threads = 4;
     long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
 
     // comm
@@ -554,6 +558,7 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_history = env_ll("history", 1);
     h->opt_gemv_ctas_per_sm = env_ll("gemv_ctas_per_sm", 0);
     h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
+    h->opt_ingest_threads = env_ll("ingest_threads", 4);
     *out = h;
     return LAMCG_OK;
 }
@@ -599,6 +604,7 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "history") h->opt_history = value;
     else if (k == "gemv_ctas_per_sm") h->opt_gemv_ctas_per_sm = value;
     else if (k == "persist_rows_smem") h->opt_persist_rows_smem = value;
+    else if (k == "ingest_threads") h->opt_ingest_threads = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->alloc_n) {
@@ -811,45 +817,67 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
     rc = alloc_system(h, rows);
     if (rc != LAMCG_OK) { close(fd); return rc; }
     const size_t n = h->n;
-    // chunked ingest: pread -> pinned double buffer -> async 2-D copy into the padded row block
+    // Chunked, multi-threaded ingest: T reader threads, each with its own stream and two pinned staging
+    // buffers, interleave over row chunks: pread (page cache / disk -> pinned) of chunk k+T overlaps the
+    // async 2-D H2D copy of chunk k.  One thread tops out near 6 GB/s (a single core's memcpy rate out of the
+    // page cache, the same rate the reference's fread reaches into pageable memory); T threads scale that
+    // until PCIe is the limit.
     const size_t row_bytes = n * sizeof(double);
-    size_t chunk_rows = std::max<size_t>(1, (size_t)(64u << 20) / row_bytes);
+    size_t chunk_rows = std::max<size_t>(1, (size_t)(32u << 20) / row_bytes);
     chunk_rows = std::min(chunk_rows, std::max<size_t>(h->local_rows, 1));
-    double *stage[2] = {nullptr, nullptr};
-    cudaEvent_t done[2];
-    auto cleanup = [&]() {
-        for (int i = 0; i < 2; ++i) { if (stage[i]) cudaFreeHost(stage[i]); cudaEventDestroy(done[i]); }
-        close(fd);
+    const size_t nchunks = (h->local_rows + chunk_rows - 1) / chunk_rows;
+    int T = (int)std::max<long long>(1, std::min<long long>(h->opt_ingest_threads, 16));
+    T = (int)std::min<size_t>((size_t)T, std::max<size_t>(nchunks, 1));
+    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * sizeof(double), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    std::atomic<int> status{LAMCG_OK};
+    std::string first_error;
+    std::mutex err_mu;
+    auto worker = [&](int t) {
+        auto failw = [&](int code, const std::string &msg) {
+            std::lock_guard<std::mutex> lk(err_mu);
+            if (status.load() == LAMCG_OK) { status.store(code); first_error = msg; }
+        };
+        if (cudaSetDevice(h->device) != cudaSuccess) return failw(LAMCG_ERR_CUDA, "cudaSetDevice failed in ingest thread");
+        cudaStream_t st = nullptr;
+        double *stage[2] = {nullptr, nullptr};
+        cudaEvent_t done[2] = {nullptr, nullptr};
+        bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
+        for (int i = 0; i < 2 && ok; ++i)
+            ok = cudaMallocHost(&stage[i], chunk_rows * row_bytes) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) failw(LAMCG_ERR_NOMEM, "cudaMallocHost of the ingest buffers failed");
+        int slot = 0;
+        for (size_t c = (size_t)t; ok && c < nchunks && status.load() == LAMCG_OK; c += (size_t)T, slot ^= 1) {
+            const size_t r = c * chunk_rows;
+            const size_t nr = std::min(chunk_rows, h->local_rows - r);
+            cudaEventSynchronize(done[slot]);
+            const off_t off = (off_t)16 + (off_t)((h->row_offset + r) * row_bytes);
+            if (pread_full(fd, stage[slot], nr * row_bytes, off) != 0) {
+                failw(LAMCG_ERR_IO, std::string(path) + ": short read in rows " + std::to_string(h->row_offset + r) + ".." +
+                                        std::to_string(h->row_offset + r + nr));
+                break;
+            }
+            cudaError_t e = cudaMemcpy2DAsync(h->A + r * h->lda, h->lda * sizeof(double), stage[slot], row_bytes, row_bytes, nr,
+                                              cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) { failw(LAMCG_ERR_CUDA, std::string("cudaMemcpy2DAsync failed: ") + cudaGetErrorString(e)); break; }
+            cudaEventRecord(done[slot], st);
+        }
+        if (st) {
+            if (cudaStreamSynchronize(st) != cudaSuccess) failw(LAMCG_ERR_CUDA, "matrix upload failed");
+            cudaStreamDestroy(st);
+        }
+        for (int i = 0; i < 2; ++i) { if (stage[i]) cudaFreeHost(stage[i]); if (done[i]) cudaEventDestroy(done[i]); }
     };
-    for (int i = 0; i < 2; ++i) cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming);
-    for (int i = 0; i < 2; ++i) {
-        if (cudaMallocHost(&stage[i], chunk_rows * row_bytes) != cudaSuccess) {
-            cleanup();
-            return h->fail(LAMCG_ERR_NOMEM, "cudaMallocHost of the ingest buffer failed");
-        }
+    {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < T; ++t) pool.emplace_back(worker, t);
+        worker(0);
+        for (auto &th : pool) th.join();
     }
-    if (h->lda != n) cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * sizeof(double), h->stream);
-    int slot = 0;
-    for (size_t r = 0; r < h->local_rows; r += chunk_rows, slot ^= 1) {
-        const size_t nr = std::min(chunk_rows, h->local_rows - r);
-        cudaEventSynchronize(done[slot]);
-        const off_t off = (off_t)16 + (off_t)((h->row_offset + r) * row_bytes);
-        if (pread_full(fd, stage[slot], nr * row_bytes, off) != 0) {
-            cudaStreamSynchronize(h->stream);
-            cleanup();
-            return h->fail(LAMCG_ERR_IO, "%s: short read in rows %zu..%zu", path, h->row_offset + r, h->row_offset + r + nr);
-        }
-        cudaError_t e = cudaMemcpy2DAsync(h->A + r * h->lda, h->lda * sizeof(double), stage[slot], row_bytes, row_bytes, nr,
-                                          cudaMemcpyHostToDevice, h->stream);
-        if (e != cudaSuccess) {
-            cleanup();
-            return h->fail(LAMCG_ERR_CUDA, "cudaMemcpy2DAsync failed: %s", cudaGetErrorString(e));
-        }
-        cudaEventRecord(done[slot], h->stream);
-    }
-    cudaError_t e = cudaStreamSynchronize(h->stream);
-    cleanup();
-    if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "matrix upload failed: %s", cudaGetErrorString(e));
+    close(fd);
+    CK(cudaSetDevice(h->device));
+    if (status.load() != LAMCG_OK) return h->fail(status.load(), "%s", first_error.c_str());
     h->has_matrix = true;
     h->has_rhs = false;
     return LAMCG_OK;
