@@ -141,27 +141,42 @@ bool plan_tma(lamcg *h, GemvPlan &p, int variant)
     return cudaFuncSetAttribute(gemv_tma_kernel<RB, CB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
 }
 
-template <int R, int U>
+template <int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0>
+bool plan_ctarow(lamcg *h, GemvPlan &p, int variant)
+{
+    p.variant = variant;
+    p.kernel = gemv_ctarow_kernel<R, U, NT, CPS, PF>;
+    p.block = NT;
+    p.smem = 0;
+    p.rows_per_pass = R;
+    int per_sm = h->opt_gemv_ctas_per_sm > 0 ? (int)h->opt_gemv_ctas_per_sm : CPS;
+    size_t want = (h->local_rows + R - 1) / R;
+    p.grid = (int)std::min<size_t>((size_t)h->sm_count * per_sm, std::max<size_t>(1, want));
+    return true;
+}
+
+template <int R, int U, int PF = 0, int CPS = 2>
 bool plan_ldg(lamcg *h, GemvPlan &p, int variant)
 {
     p.variant = variant;
-    p.kernel = gemv_ldg_kernel<R, U>;
+    p.kernel = gemv_ldg_kernel<R, U, PF, CPS>;
     p.block = kLdgWarps * 32;
     p.smem = kLdgSmemBytes;
     p.rows_per_pass = kLdgWarps * R;
-    int per_sm = h->opt_gemv_ctas_per_sm > 0 ? (int)h->opt_gemv_ctas_per_sm : 2;
+    int per_sm = h->opt_gemv_ctas_per_sm > 0 ? (int)h->opt_gemv_ctas_per_sm : CPS;
     size_t want = (h->local_rows + p.rows_per_pass - 1) / p.rows_per_pass;
     p.grid = (int)std::min<size_t>((size_t)h->sm_count * per_sm, std::max<size_t>(1, want));
-    return cudaFuncSetAttribute(gemv_ldg_kernel<R, U>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
+    return cudaFuncSetAttribute(gemv_ldg_kernel<R, U, PF, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
 }
 
 // Variant ids: 1x = ldg family, 2x = tma-ring family.  0 = auto.
 int make_plan(lamcg *h)
 {
     int v = (int)h->opt_gemv_variant;
-    // measured on B200 (profiles/r01_sweep2.log): ldg<4,4> is the fastest on tall blocks (7216 GB/s at 100000 rows),
-    // ldg<2,8> on short ones (7116 GB/s at 12500 rows, where 32-row passes leave a ragged tail)
-    if (v == 0) v = h->local_rows >= 40000 ? 11 : 14;
+    // measured on B200 (profiles/r01_sweep3-5.log): the "cta rows" kernel with 512 threads, 1 CTA/SM, 8 rows in
+    // flight is the fastest on tall blocks (7.3-7.4 TB/s at 100000 and 12500 rows); on short blocks the
+    // 256-thread, 2 CTA/SM shape balances better (6.5-6.7 TB/s at 10000 rows)
+    if (v == 0) v = h->local_rows >= 12000 ? 36 : 32;
     bool ok = false;
     GemvPlan p;
     switch (v) {
@@ -174,6 +189,28 @@ int make_plan(lamcg *h)
     case 16: ok = plan_ldg<1, 8>(h, p, v); break;
     case 17: ok = plan_ldg<4, 8>(h, p, v); break;
     case 18: ok = plan_ldg<2, 16>(h, p, v); break;
+    case 31: ok = plan_ctarow<4>(h, p, v); break;
+    case 32: ok = plan_ctarow<8>(h, p, v); break;
+    case 33: ok = plan_ctarow<2>(h, p, v); break;
+    case 34: ok = plan_ctarow<8, 2>(h, p, v); break;
+    case 35: ok = plan_ctarow<16, 2>(h, p, v); break;
+    case 36: ok = plan_ctarow<8, 4, 512, 1>(h, p, v); break;
+    case 37: ok = plan_ctarow<8, 2, 512, 1>(h, p, v); break;
+    case 38: ok = plan_ctarow<8, 4, 128, 4>(h, p, v); break;
+    case 39: ok = plan_ctarow<12, 2>(h, p, v); break;
+    case 30: ok = plan_ctarow<16, 1>(h, p, v); break;
+    case 61: ok = plan_ctarow<8, 4, 1024, 1>(h, p, v); break;
+    case 62: ok = plan_ctarow<4, 4, 1024, 1>(h, p, v); break;
+    case 63: ok = plan_ctarow<4, 8, 512, 1>(h, p, v); break;
+    case 65: ok = plan_ctarow<16, 2, 512, 1>(h, p, v); break;
+    case 67: ok = plan_ctarow<6, 4, 512, 1>(h, p, v); break;
+    case 68: ok = plan_ctarow<8, 4, 768, 1>(h, p, v); break;
+    case 69: ok = plan_ctarow<4, 4, 512, 1>(h, p, v); break;
+    case 70: ok = plan_ctarow<8, 4, 512, 1, 1>(h, p, v); break;
+    case 41: ok = plan_ldg<4, 4, 1>(h, p, v); break;
+    case 44: ok = plan_ldg<2, 8, 1>(h, p, v); break;
+    case 51: ok = plan_ldg<1, 8, 0, 3>(h, p, v); break;
+    case 52: ok = plan_ldg<2, 4, 0, 3>(h, p, v); break;
     case 2: ok = plan_tma<16, 256, 6>(h, p, v); break;
     case 21: ok = plan_tma<8, 256, 12>(h, p, v); break;
     case 22: ok = plan_tma<32, 128, 6>(h, p, v); break;

@@ -185,6 +185,16 @@ __device__ __forceinline__ double2 ldg_stream_f64x2(const double *ptr, uint64_t 
     return v;
 }
 
+// same, asking L2 to fetch 256 bytes per miss (two adjacent 128-byte lines share a DRAM burst)
+__device__ __forceinline__ double2 ldg_stream_f64x2_pf256(const double *ptr, uint64_t policy)
+{
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::256B.v2.f64 {%0, %1}, [%2], %3;"
+                 : "=d"(v.x), "=d"(v.y)
+                 : "l"(ptr), "l"(policy));
+    return v;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

@@ -206,8 +206,8 @@ constexpr int kLdgPChunk = 2048;
 constexpr int kLdgPStages = 3;
 constexpr size_t kLdgSmemBytes = (size_t)kLdgPStages * kLdgPChunk * 8 + 2 * kLdgPStages * 8 + kLdgWarps * 8 + 64;
 
-template <int R, int U>
-__global__ void __launch_bounds__(kLdgWarps * 32, 2) gemv_ldg_kernel(GemvArgs g)
+template <int R, int U, int PF = 0, int CPS = 2>
+__global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs g)
 {
     constexpr int NW = kLdgWarps, PCH = kLdgPChunk, PST = kLdgPStages;
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) gemv_ldg_kernel(GemvArgs g)
                         const bool cv = cc < nc;
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            if (cv && r < nr) a[r][u] = ldg_stream_f64x2(arow[r] + c0 + cc, polA);
+                            if (cv && r < nr) a[r][u] = PF ? ldg_stream_f64x2_pf256(arow[r] + c0 + cc, polA) : ldg_stream_f64x2(arow[r] + c0 + cc, polA);
                             else a[r][u] = make_double2(0.0, 0.0);
                         }
                         pv[u] = cv ? *reinterpret_cast<const double2 *>(pb + cc) : make_double2(0.0, 0.0);
@@ -331,6 +331,88 @@ __global__ void __launch_bounds__(kLdgWarps * 32, 2) gemv_ldg_kernel(GemvArgs g)
         }
         grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane, &g.pv, 0, g.par, seq);
     }
+}
+
+// =============================================================================================
+// K1, variant 3 ("cta rows"): the whole CTA sweeps one row at a time, R rows in flight.
+// Thread t owns columns {2t, 2t+1} + 512k of every 2048-column chunk: one CTA-wide load instruction covers
+// 4 KB of contiguous row, a chunk of one row is 16 KB contiguous.  The thread's 4 double2 of p for the chunk
+// sit in registers and are reused for the R rows (p is read from L2 once per R rows); R accumulators per
+// thread are reduced across the CTA at the end of the pass.  No shared-memory staging, no mbarriers.
+// =============================================================================================
+template <int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0>
+__global__ void __launch_bounds__(NT, CPS) gemv_ctarow_kernel(GemvArgs g)
+{
+    constexpr int CH = NT * U * 2; // columns per chunk (2048 for the default shape)
+    constexpr int NWARP = NT / 32;
+    static_assert(R <= 32, "row sums are finished by one warp");
+    __shared__ double red[NWARP][R];
+    if (g.check_done && ld_volatile_int(&g.st->done)) return;
+    const unsigned long long seq = gemv_peer_prologue(g);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const long long base = g.rows / G, rem = g.rows % G;
+    const long long r0 = bid * base + (bid < rem ? bid : rem);
+    const long long rcnt = base + (bid < rem ? 1 : 0);
+    const uint64_t polA = l2_policy_evict_first();
+    double cta_dot = 0.0;
+    for (long long pr = 0; pr < rcnt; pr += R) {
+        const int nr = rcnt - pr < R ? (int)(rcnt - pr) : R;
+        const double *arow0 = g.A + (r0 + pr) * g.lda;
+        double acc[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = 0.0;
+        for (long long c0 = 0; c0 < g.lda; c0 += CH) {
+            double2 pv[U];
+            bool cv[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const long long c = c0 + 2 * tid + (long long)u * NT * 2;
+                cv[u] = c < g.lda;
+                pv[u] = cv[u] ? __ldg(reinterpret_cast<const double2 *>(g.p + c)) : make_double2(0.0, 0.0);
+            }
+            double2 a[R][U];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const long long c = c0 + 2 * tid + (long long)u * NT * 2;
+                    a[r][u] = (cv[u] && r < nr) ? (PF ? ldg_stream_f64x2_pf256(arow0 + (long long)r * g.lda + c, polA)
+                                                      : ldg_stream_f64x2(arow0 + (long long)r * g.lda + c, polA))
+                                                : make_double2(0.0, 0.0);
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    acc[r] = mul_add(a[r][u].x, pv[u].x, acc[r]);
+                    acc[r] = mul_add(a[r][u].y, pv[u].y, acc[r]);
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+        if (lane == 0) {
+#pragma unroll
+            for (int r = 0; r < R; ++r) red[warp][r] = acc[r];
+        }
+        __syncthreads();
+        if (warp == 0) {
+            double contrib = 0.0;
+            if (lane < nr) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) sum = __dadd_rn(sum, red[w][lane]);
+                g.Ap[r0 + pr + lane] = sum;
+                contrib = __dmul_rn(g.p[g.row_offset + r0 + pr + lane], sum);
+            }
+            contrib = warp_sum(contrib);
+            cta_dot = __dadd_rn(cta_dot, contrib);
+        }
+        __syncthreads();
+    }
+    if (warp == 0) grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane, &g.pv, 0, g.par, seq);
 }
 
 // =============================================================================================

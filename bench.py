@@ -272,9 +272,11 @@ def run_b200_arm(args):
         peak, peak_src = measured_peaks()
         traffic = None
         tpath = os.path.join(REPO, "profiles", "gemv_traffic.json")
-        if os.path.exists(tpath):
+        if os.path.exists(tpath):  # ncu capture of this kernel on this workload; only valid for the same n and rank count
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_per_launch")
+                tj = json.load(f)
+            if tj.get("n") == n and tj.get("ranks") == world:
+                traffic = tj.get("dram_bytes_per_launch")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * dev_s_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
