@@ -72,6 +72,38 @@ def main():
             return oracle.cg_solve(A, b, 1000, 1e-9)
         return mk
 
+    def spd_files(n, seed, tmpdir):
+        """File mode with one rank per GPU: every rank preads ONLY its own row block (64-bit offsets), rank 0
+        saves the gathered x; layout-1 set_matrix (caller passes just the local block) must give the same bits."""
+        A, b = random_spd.random_spd_system(n, seed)
+        pa, pb, px = (os.path.join(tmpdir, f"{comm}_{k}.bin") for k in "Abx")
+        if rank == 0:
+            fileformat.write_matrix(pa, A)
+            fileformat.write_matrix(pb, b)
+        dist.barrier()
+
+        def mk(s):
+            s.load_matrix(pa)
+            s.load_rhs(pb)
+            r = s.solve(1000, 1e-9)
+            x_file = s.solution().copy()
+            s.save_solution(px)          # collective; rank 0 writes
+            dist.barrier()
+            assert fileformat.read_header(px) == (n, 1)
+            assert np.array_equal(fileformat.read_vector(px), x_file)
+            rows, off = lamcg_b200.launch.partition(n, world, rank)
+            s.set_matrix(np.ascontiguousarray(A[off:off + rows]), layout=1)
+            s.set_rhs(b)
+            r2 = s.solve(1000, 1e-9)
+            assert r2.iterations == r.iterations and np.array_equal(s.solution(), x_file)
+            s.load_matrix(pa)            # back to the file system for the caller's solve
+            s.load_rhs(pb)
+            return oracle.cg_solve(A, b, 1000, 1e-9)
+        return mk
+
+    import tempfile
+    tmpdir = os.environ.get("LAMCG_TEST_TMP") or tempfile.gettempdir()
+    case("spd_from_files", 1500, spd_files(1500, 5, tmpdir), 1000, 2, 1e-9)
     case("gen_even", 4096, gen(4096, 300), 300, 2, 1e-12)
     case("gen_remainder", 10007, gen(10007, 200), 200, 1, 1e-12)      # n % P != 0: last rank owns the remainder
     case("gen_converge", 1000, gen(1000, 10000), 10000, 2, 1e-12)     # done latch trips on all ranks at iteration 500

@@ -63,3 +63,31 @@ def test_cpp_driver_forked_ranks(comm, tmp_path):
     assert math.isclose(float(f[7]), o.rel, rel_tol=2e-5)
     x = fileformat.read_vector(sol)
     assert np.linalg.norm(x - o.x) / np.linalg.norm(o.x) <= 1e-12
+
+
+def test_cpp_positional_multi_gpu_driver(tmp_path):
+    """test_CG_MultiGPUS_CUDA.out (positional, file mode) with 2 forked ranks against the oracle."""
+    if _ngpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    import numpy as np
+    import oracle
+    import parity_util
+    from oracle import fileformat, random_spd
+    exe = os.path.join(REPO, "2024-eumaster4hpc-student-challenge_b200", "test", "test_CG_MultiGPUS_CUDA.out")
+    n = 777
+    A, b = random_spd.random_spd_system(n, 3)
+    pa, pb, px = (str(tmp_path / f) for f in ("A.bin", "b.bin", "x.bin"))
+    fileformat.write_matrix(pa, A)
+    fileformat.write_matrix(pb, b)
+    o = oracle.cg_solve(A, b, 1000, 1e-9)
+    for comm in ("peer", "nccl"):
+        env = dict(os.environ, LAMCG_NGPUS="2", LAMCG_COMM=comm)
+        res = subprocess.run([exe, pa, pb, px, "1000", "1e-9"], capture_output=True, text=True, env=env, timeout=200)
+        assert res.returncode == 0, res.stdout + res.stderr
+        assert "Converged in" in res.stdout and "Finished successfully" in res.stdout and "GPUs (ranks):      2" in res.stdout
+        x = fileformat.read_vector(px)
+        assert np.linalg.norm(x - o.x) / np.linalg.norm(o.x) <= 1e-9
+        res = subprocess.run([exe, pa, pb, px, str(o.iters), "0"], capture_output=True, text=True, env=env, timeout=200)
+        om = oracle.cg_solve(A, b, o.iters, 0.0)
+        x = fileformat.read_vector(px)
+        assert np.linalg.norm(x - om.x) / np.linalg.norm(om.x) <= parity_util.X_TOL_FILE
