@@ -88,10 +88,19 @@ public:
             }
         }
         if (!peer) {
+            // NCCL prints its version banner on stdout when NCCL_DEBUG is set; stdout must carry exactly the
+            // reference's CSV line, so fd 1 points at stderr while the communicator is created.
+            std::fflush(stdout);
+            std::cout.flush();
+            const int saved_stdout = dup(1);
+            dup2(2, 1);
             unsigned char id[LAMCG_NCCL_ID_BYTES] = {0};
             if (world.rank() == 0 && lamcg_comm_nccl_unique_id(id) != LAMCG_OK) std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
             world.bcast(id, sizeof id, 0);
             check(lamcg_comm_init_nccl(h_, id));
+            std::fflush(stdout);
+            dup2(saved_stdout, 1);
+            close(saved_stdout);
         }
         world.barrier();
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
