@@ -89,6 +89,8 @@ _SIGNATURES = {
     "lamcg_load_rhs": (ctypes.c_int, [_vp, _cp]),
     "lamcg_set_matrix": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t, ctypes.c_int]),
     "lamcg_set_rhs": (ctypes.c_int, [_vp, _vp, ctypes.c_size_t]),
+    "lamcg_random_spd_system": (ctypes.c_int, [_vp, ctypes.c_size_t, ctypes.c_int]),
+    "lamcg_save_system": (ctypes.c_int, [_vp, _cp, _cp]),
     "lamcg_solve": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.POINTER(lamcg_result)]),
     "lamcg_get_residual_history": (ctypes.c_int, [_vp, _dp, ctypes.c_int]),
     "lamcg_get_solution_local": (ctypes.c_int, [_vp, _dp]),
@@ -224,6 +226,13 @@ class Solver:
         else:
             arr = _as_f64(b, "b").reshape(-1)
             self._ck(self._L.lamcg_set_rhs(self._h, _vp(arr.ctypes.data), arr.size))
+
+    def random_spd_system(self, n: int, seed: int) -> None:
+        """GPU version of the reference's random_spd_system tool (fills A and b of this handle)."""
+        self._ck(self._L.lamcg_random_spd_system(self._h, n, seed))
+
+    def save_system(self, matrix_path: str, rhs_path: str) -> None:
+        self._ck(self._L.lamcg_save_system(self._h, os.fsencode(matrix_path), os.fsencode(rhs_path)))
 
     # -- solve
     def solve(self, max_iters: int, rel_error: float) -> lamcg_result:

@@ -22,6 +22,7 @@
 
 #include "../../include/lamcg.h"
 #include "lamcg_kernels.cuh"
+#include "lamcg_spd.cuh"
 #include "nccl_dyn.h"
 
 using namespace lamcgk;
@@ -82,6 +83,7 @@ struct lamcg {
     size_t peer_bytes = 0, peer_n = 0;
     PeerView pv{};
     unsigned long long seq_next = 1, gather_seq = 0;
+    double *gemm_ws = nullptr; // split-K workspace of the SPD generator (alive only inside lamcg_random_spd_system)
     unsigned long long *persist_ll = nullptr; // [2][G][G][2] tagged partial words (per-CTA inboxes)
     int persist_ll_grid = 0;
 
@@ -1120,6 +1122,154 @@ int lamcg_save_solution(lamcg_t *h, const char *path)
     bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1 && fwrite(x.data(), sizeof(double), h->n, f) == h->n;
     ok = (fclose(f) == 0) && ok;
     if (!ok) return h->fail(LAMCG_ERR_IO, "short write to %s", path);
+    return LAMCG_OK;
+}
+
+// ---- random SPD system generator (reference: challenge/main/random_spd_system.cpp) ----
+namespace {
+
+constexpr long long kGemmWsTile = 512 * 512; // largest M*N that takes the split-K path
+
+int launch_gemm(lamcg *h, const double *A, const double *B, double *C, long long M, long long N, long long K, long long sai,
+                long long sak, long long sbk, long long sbj, long long sci, long long scj, double alpha, double beta)
+{
+    if (M <= 0 || N <= 0) return LAMCG_OK;
+    GemmArgs g{A, B, C, M, N, K, sai, sak, sbk, sbj, sci, scj, alpha, beta, 0, nullptr};
+    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
+    // skinny products (the Q1^T Q2 of the lower Gram-Schmidt levels: few output tiles, long K) are split along K
+    // over up to 128 CTAs; slices are summed in slice order by a second kernel, so the result stays deterministic
+    const long long tiles = (long long)grid.x * grid.y;
+    if (h->gemm_ws && tiles < h->sm_count && K >= 2048 && M * N <= kGemmWsTile) {
+        int slices = (int)std::min<long long>({128, K / 512, (long long)(2 * h->sm_count) / tiles});
+        if (slices >= 2) {
+            g.k_slice = ((K + slices - 1) / slices + 15) / 16 * 16;
+            slices = (int)((K + g.k_slice - 1) / g.k_slice);
+            g.ws = h->gemm_ws;
+            grid.z = (unsigned)slices;
+            gemm_f64_kernel<<<grid, 256, 0, h->stream>>>(g);
+            CK(cudaGetLastError());
+            gemm_splitk_reduce_kernel<<<(unsigned)std::min<long long>((M * N + 255) / 256, 1024), 256, 0, h->stream>>>(g, slices);
+            CK(cudaGetLastError());
+            return LAMCG_OK;
+        }
+    }
+    gemm_f64_kernel<<<grid, 256, 0, h->stream>>>(g);
+    CK(cudaGetLastError());
+    return LAMCG_OK;
+}
+
+// random_spd_system.cpp:41-62 — recursive block Gram-Schmidt on the columns [c0, c1) of the column-major Q (ld = n)
+int gram_schmidt(lamcg *h, double *Q, long long n, long long c0, long long c1, double *buf)
+{
+    const long long cnt = c1 - c0;
+    if (cnt == 1) {
+        normalize_column_kernel<<<1, 256, 0, h->stream>>>(Q + c0 * n, n);
+        CK(cudaGetLastError());
+        return LAMCG_OK;
+    }
+    const long long mid = (c0 + c1) / 2, n1 = mid - c0, n2 = c1 - mid;
+    int rc = gram_schmidt(h, Q, n, c0, mid, buf);
+    if (rc != LAMCG_OK) return rc;
+    const double *Q1 = Q + c0 * n;
+    double *Q2 = Q + mid * n;
+    // buf (n1 x n2, column-major, ld n1) = Q1^T Q2 ; Q2 -= Q1 buf
+    rc = launch_gemm(h, Q1, Q2, buf, n1, n2, n, /*sai*/ n, /*sak*/ 1, /*sbk*/ 1, /*sbj*/ n, /*sci*/ 1, /*scj*/ n1, 1.0, 0.0);
+    if (rc != LAMCG_OK) return rc;
+    rc = launch_gemm(h, Q1, buf, Q2, n, n2, n1, /*sai*/ 1, /*sak*/ n, /*sbk*/ 1, /*sbj*/ n1, /*sci*/ 1, /*scj*/ n, -1.0, 1.0);
+    if (rc != LAMCG_OK) return rc;
+    return gram_schmidt(h, Q, n, mid, c1, buf);
+}
+
+// random_spd_system.cpp:27-38 — glibc stream, column-major fill
+void host_random_fill(double *out, size_t count, int seed)
+{
+    srand((unsigned)seed);
+    for (size_t i = 0; i < count; ++i) out[i] = ((2.0 * rand()) / RAND_MAX) - 1.0;
+}
+
+} // namespace
+
+int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
+{
+    if (!h || n == 0) return LAMCG_ERR_INVALID;
+    if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "the SPD generator runs on one rank (generate, save, then load row blocks)");
+    int rc = alloc_system(h, n);
+    if (rc != LAMCG_OK) return rc;
+    double *Q = nullptr, *buf = nullptr, *d_dev = nullptr;
+    auto cleanup = [&]() { cudaFree(Q); cudaFree(buf); cudaFree(d_dev); cudaFree(h->gemm_ws); h->gemm_ws = nullptr; };
+    if (cudaMalloc(&h->gemm_ws, (size_t)128 * kGemmWsTile * sizeof(double)) != cudaSuccess) { cudaGetLastError(); h->gemm_ws = nullptr; }
+    const size_t half = (n + 1) / 2;
+    if (cudaMalloc(&Q, n * n * sizeof(double)) != cudaSuccess || cudaMalloc(&buf, (half * half + 1) * sizeof(double)) != cudaSuccess ||
+        cudaMalloc(&d_dev, n * sizeof(double)) != cudaSuccess) {
+        cudaGetLastError();
+        cleanup();
+        return h->fail(LAMCG_ERR_NOMEM, "device allocation for the %zu x %zu generator workspace failed", n, n);
+    }
+    {   // Q <- U(-1,1), seed (host stream, chunked upload so host memory stays small)
+        const size_t chunk = std::min<size_t>(n * n, (size_t)1 << 24);
+        std::vector<double> stage(chunk);
+        srand((unsigned)seed);
+        for (size_t off = 0; off < n * n; off += chunk) {
+            const size_t cnt = std::min(chunk, n * n - off);
+            for (size_t i = 0; i < cnt; ++i) stage[i] = ((2.0 * rand()) / RAND_MAX) - 1.0;
+            cudaError_t e = cudaMemcpy(Q + off, stage.data(), cnt * sizeof(double), cudaMemcpyHostToDevice);
+            if (e != cudaSuccess) { cleanup(); return h->fail(LAMCG_ERR_CUDA, "upload of the random matrix failed: %s", cudaGetErrorString(e)); }
+        }
+    }
+    rc = gram_schmidt(h, Q, (long long)n, 0, (long long)n, buf);
+    if (rc != LAMCG_OK) { cleanup(); return rc; }
+    {   // eigenvalues exp(3.5 U), seed - 10 ; scale column c by sqrt(D[c])
+        std::vector<double> d(n);
+        host_random_fill(d.data(), n, seed - 10);
+        for (size_t i = 0; i < n; ++i) d[i] = std::exp(3.5 * d[i]);
+        cudaError_t e = cudaMemcpyAsync(d_dev, d.data(), n * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        if (e != cudaSuccess) { cleanup(); return h->fail(LAMCG_ERR_CUDA, "upload of the eigenvalues failed: %s", cudaGetErrorString(e)); }
+        scale_columns_kernel<<<std::min(h->sm_count * 8, kMaxGrid), 256, 0, h->stream>>>(Q, d_dev, (long long)n);
+    }
+    // A = Y Y^T into the padded row-major block (symmetric, so row-major == the reference's column-major file)
+    if (h->lda != n) cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * sizeof(double), h->stream);
+    rc = launch_gemm(h, Q, Q, h->A, (long long)n, (long long)n, (long long)n, /*sai*/ 1, /*sak*/ (long long)n, /*sbk*/ (long long)n,
+                     /*sbj*/ 1, /*sci*/ (long long)h->lda, /*scj*/ 1, 1.0, 0.0);
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    cleanup();
+    if (rc != LAMCG_OK) return rc;
+    if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "the SPD generator faulted on the device: %s", cudaGetErrorString(se));
+    h->has_matrix = true;
+    std::vector<double> b(n);
+    host_random_fill(b.data(), n, seed + 10); // random_spd_system.cpp:166
+    return lamcg_set_rhs(h, b.data(), n);
+}
+
+int lamcg_save_system(lamcg_t *h, const char *matrix_path, const char *rhs_path)
+{
+    if (!h || !matrix_path || !rhs_path) return LAMCG_ERR_INVALID;
+    if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "save_system runs on one rank");
+    if (!h->has_matrix || !h->has_rhs) return h->fail(LAMCG_ERR_STATE, "no system to save");
+    CK(cudaSetDevice(h->device));
+    const size_t n = h->n;
+    const uint64_t hdrA[2] = {(uint64_t)n, (uint64_t)n}, hdrb[2] = {(uint64_t)n, 1ull};
+    FILE *f = fopen(matrix_path, "wb");
+    if (!f) return h->fail(LAMCG_ERR_IO, "Cannot open output file %s: %s", matrix_path, strerror(errno));
+    bool ok = fwrite(hdrA, sizeof hdrA, 1, f) == 1;
+    const size_t chunk_rows = std::max<size_t>(1, ((size_t)64 << 20) / (n * sizeof(double)));
+    std::vector<double> stage(chunk_rows * n);
+    for (size_t r = 0; ok && r < n; r += chunk_rows) {
+        const size_t nr = std::min(chunk_rows, n - r);
+        cudaError_t e = cudaMemcpy2D(stage.data(), n * sizeof(double), h->A + r * h->lda, h->lda * sizeof(double), n * sizeof(double), nr,
+                                     cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) { fclose(f); return h->fail(LAMCG_ERR_CUDA, "download of the matrix failed: %s", cudaGetErrorString(e)); }
+        ok = fwrite(stage.data(), sizeof(double), nr * n, f) == nr * n;
+    }
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return h->fail(LAMCG_ERR_IO, "short write to %s", matrix_path);
+    std::vector<double> b(n);
+    CK(cudaMemcpy(b.data(), h->b_full, n * sizeof(double), cudaMemcpyDeviceToHost));
+    f = fopen(rhs_path, "wb");
+    if (!f) return h->fail(LAMCG_ERR_IO, "Cannot open output file %s: %s", rhs_path, strerror(errno));
+    ok = fwrite(hdrb, sizeof hdrb, 1, f) == 1 && fwrite(b.data(), sizeof(double), n, f) == n;
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) return h->fail(LAMCG_ERR_IO, "short write to %s", rhs_path);
     return LAMCG_OK;
 }
 

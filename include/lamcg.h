@@ -114,6 +114,14 @@ int lamcg_load_rhs(lamcg_t *h, const char *path);
 int lamcg_set_matrix(lamcg_t *h, const double *A, size_t n, int layout);
 int lamcg_set_rhs(lamcg_t *h, const double *b, size_t n);
 
+/* Random SPD system like challenge/main/random_spd_system.cpp (there: Intel MKL on the host):
+ * Q = recursive block Gram-Schmidt of a U(-1,1) matrix drawn with glibc srand(seed)/rand(),
+ * eigenvalues exp(3.5 U) (seed - 10), A = (Q sqrt(D))(Q sqrt(D))^T, rhs U(-1,1) (seed + 10).  The random
+ * streams are drawn on the host, every O(n^3) step runs on the GPU.  Single rank. */
+int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed);
+/* Write the current system in the reference's binary format (random_spd_system.cpp:105-121). Single rank. */
+int lamcg_save_system(lamcg_t *h, const char *matrix_path, const char *rhs_path);
+
 /* ---- solve ---------------------------------------------------------------------------------- */
 /* solve(max_iters, rel_error) (OMP.hpp:49-91): x0 = 0, r = p = b; may be called repeatedly. */
 int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out);
