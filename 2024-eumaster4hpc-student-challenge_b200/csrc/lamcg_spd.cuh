@@ -6,7 +6,7 @@
 // which is what makes a seed reproduce the reference's draws) and every O(n^3) step runs on the GPU:
 // one strided fp64 GEMM kernel serves Q1^T Q2, Q2 -= Q1 C and Y Y^T.  This is a setup tool, not the
 // hot path; fused multiply-add is used (the generator's output is "parity unpinned": no reference
-// test pins MKL's bits, see oracle/random_spd.py).
+// test pins MKL's bits).
 #pragma once
 
 #include "lamcg_device.cuh"
