@@ -501,6 +501,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
         out->gemv_seconds = 0.0;
         out->iterations_run = s.iters_done;
         out->kernel_launches = 1;
+        out->numerical_breakdown = s.breakdown;
     }
     return LAMCG_OK;
 }
@@ -1053,6 +1054,7 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
         out->gemv_seconds = gemv_ms * 1e-3;
         out->iterations_run = s.iters_done;
         out->kernel_launches = launches;
+        out->numerical_breakdown = s.breakdown;
     }
     return LAMCG_OK;
 }

@@ -29,6 +29,7 @@ struct DevState {
     int max_iters;
     int done;          // latch: once set every later kernel of the loop is a no-op
     int converged;
+    int breakdown;     // stopped on a non-finite residual / beta
     int iters_done;
     int error;         // 0 ok | 1 mbarrier timeout | 2 peer-flag timeout
     int hist_cap;

@@ -501,7 +501,11 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
     const int it = it0 + 1;
     const double rel = sqrt(rr_new / st->bb);
     const bool conv = rel < st->eps;
-    const bool fin = conv || it >= st->max_iters;
+    // Non-finite scalars (b = 0, a matrix that is not SPD, overflow) can never satisfy the stop test: the
+    // reference keeps iterating on NaNs until max_iters and prints "max_iters+1, nan" (TESTS/BEST_RESULTS:114).
+    // Same report here, without burning the remaining iterations.
+    const bool broke = !(rel == rel) || isinf(rel) || !(beta == beta);
+    const bool fin = conv || broke || it >= st->max_iters;
 
     if (!fin) {
         const double *p = v.p_in + v.row_offset;
@@ -539,6 +543,7 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
         if (v.hist && it - 1 < st->hist_cap) v.hist[it - 1] = rel;
         if (fin) {
             st->converged = conv ? 1 : 0;
+            st->breakdown = broke ? 1 : 0;
             __threadfence();
             st->done = 1;
         }
@@ -621,6 +626,7 @@ __global__ void __launch_bounds__(1024) init_solve_kernel(InitArgs a)
         st->max_iters = a.max_iters;
         st->done = a.max_iters <= 0 ? 1 : 0;
         st->converged = 0;
+        st->breakdown = 0;
         st->iters_done = 0;
         st->error = 0;
         st->hist_cap = a.hist_cap;
@@ -848,7 +854,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
 
     double rr = bb, beta = 0.0;
     int it;
-    bool converged = false;
+    bool converged = false, broke = false;
     long long ph[6] = {0, 0, 0, 0, 0, 0}; // phase timers (CTA 0 thread 0 reports): p update, GEMV, row sums, p.Ap exchange, x/r update, r.r exchange
     long long tc = clock64();
 #define LAMCG_PHASE(k) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; }
@@ -916,21 +922,24 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
             const double rel0 = sqrt(rrn_w0 / bb);
             s_scal[1] = rrn_w0 / rr; // beta = rr_new / rr
             s_scal[2] = rrn_w0;
-            s_scal[3] = rel0 < a.eps ? 1.0 : 0.0;
+            const bool broke0 = !(rel0 == rel0) || isinf(rel0) || !(s_scal[1] == s_scal[1]);
+            s_scal[3] = rel0 < a.eps ? 1.0 : (broke0 ? 2.0 : 0.0);
             if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
         }
         __syncthreads();
         beta = s_scal[1];
         rr = s_scal[2];
         LAMCG_PHASE(5)
-        if (s_scal[3] != 0.0) { converged = true; break; }
+        if (s_scal[3] == 1.0) { converged = true; break; }
+        if (s_scal[3] == 2.0) { broke = true; break; }
     }
     if (tid < rcnt) a.x[r0 + tid] = x_own;
     if (bid == 0 && tid == 0) {
         st->bb = bb;
         st->rr_final = rr;
-        st->iters_done = converged ? it : (a.max_iters > 0 ? a.max_iters : 0);
+        st->iters_done = (converged || broke) ? it : (a.max_iters > 0 ? a.max_iters : 0);
         st->converged = converged ? 1 : 0;
+        st->breakdown = broke ? 1 : 0;
         st->max_iters = a.max_iters;
         st->eps = a.eps;
         st->done = 1;

@@ -51,6 +51,8 @@ typedef struct {
     double gemv_seconds;   /* summed device time of the GEMV launches; 0 unless option time_gemv=1 */
     int iterations_run;    /* iterations actually executed on the device (== min(iterations,max_iters)) */
     int kernel_launches;   /* kernels of this library launched by this solve (incl. graph nodes) */
+    int numerical_breakdown; /* 1: stopped early on a non-finite residual (b = 0, A not SPD): reported like the
+                              reference would after max_iters NaN iterations: converged 0, max_iters+1, nan */
 } lamcg_result;
 
 typedef struct {

@@ -407,3 +407,22 @@ def test_persistent_loop_agrees_with_graph_loop_on_spd(solver):
     check_matched_iterations(solver, A, b, o.iters, "persistent_spd_n1536")
     r = solver.solve(0, 1e-9)
     assert not r.converged and r.iterations == 1 and r.iterations_run == 0
+
+
+@pytest.mark.parametrize("loop_mode", [1, 2, 3])
+def test_non_finite_systems_report_like_the_reference(solver, loop_mode):
+    """b = 0 gives rr/bb = 0/0: the reference iterates on NaNs to the end and reports max_iters+1 and nan
+    (the `10001,-nan` rows of TESTS/BEST_RESULTS:114).  Same report, but the loop stops at once."""
+    n = 64
+    solver.set_option("loop_mode", loop_mode)
+    solver.set_matrix(oracle.generate_matrix(n))
+    solver.set_rhs(np.zeros(n))
+    r = solver.solve(500, 1e-9)
+    o = oracle.cg_solve(oracle.generate_matrix(n), np.zeros(n), 500, 1e-9)
+    assert not r.converged and not o.converged
+    assert r.iterations == o.iters == 501 and math.isnan(r.rel_residual) and math.isnan(o.rel)
+    assert r.numerical_breakdown == 1 and r.iterations_run == 1
+    # a healthy system afterwards on the same handle
+    solver.set_rhs(np.ones(n))
+    r = solver.solve(500, 1e-9)
+    assert r.converged and r.numerical_breakdown == 0 and r.iterations == 32
