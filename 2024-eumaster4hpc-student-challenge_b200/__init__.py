@@ -277,8 +277,8 @@ class Solver:
         return ms.value
 
     def loop_profile(self) -> list[int]:
-        """SM cycles per phase of the last persistent-loop solve (CTA 0): p update, GEMV, row sums,
-        p.Ap exchange, x/r update, r.r exchange."""
+        """SM cycles per phase of the last persistent-loop solve (CTA 0): p update, GEMV, row sums + p.Ap
+        exchange, alpha broadcast, x/r update + r.r exchange, beta broadcast."""
         buf = (ctypes.c_longlong * 8)()
         cnt = self._ck(self._L.lamcg_get_loop_profile(self._h, buf, 8))
         return [int(buf[i]) for i in range(min(cnt, 6))]

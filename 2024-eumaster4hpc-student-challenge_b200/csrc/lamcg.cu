@@ -440,7 +440,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     if (h->n > kPersistMaxN) return h->fail(LAMCG_ERR_INVALID, "the persistent loop supports n <= %zu", kPersistMaxN);
 
     const int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
-    const size_t ll_words = (size_t)4 * grid * grid;
+    const size_t ll_words = (size_t)2 * kLLStride * grid * grid;
     if (!h->persist_ll || h->persist_ll_grid < grid) {
         cudaFree(h->persist_ll);
         h->persist_ll = nullptr;

@@ -727,6 +727,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned 
     return v;
 }
 
+// Tagged-word traffic of the persistent loop: strong (gpu-scope) accesses that bypass L1.  Measured: strong
+// loads of one thread are NOT pipelined (10 of them in a row cost ~4000 cycles, i.e. ~400 each), so every
+// exchange is arranged to need ONE 16-byte load and ONE 16-byte store per thread.
 __device__ __forceinline__ void st_relaxed_gpu_u64(unsigned long long *p, unsigned long long v)
 {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -736,6 +739,14 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned 
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu_v2u64(unsigned long long *p, unsigned long long a, unsigned long long b)
+{
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(a), "l"(b) : "memory");
+}
+__device__ __forceinline__ void ld_relaxed_gpu_v2u64(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
+{
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
 
 // Grid-wide "all-gather + fixed-order sum" that doubles as the grid barrier, in ONE L2 round trip.
@@ -748,6 +759,7 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu_u64(const unsigned 
 // and are added in index order, so every CTA gets the same bits.  Everything a CTA wrote before the
 // call (its r slice) is visible to all CTAs after it.
 constexpr int kPersistMaxGrid = 256;
+constexpr int kLLStride = 16; // 8-byte words per (dst, src) slot: one 128-byte line each, so a line has one writer and one reader
 
 // kPublishes: the CTA wrote global data (its r slice) that the other CTAs read after this call, so the
 // stores need a release fence before and the polls an acquire fence after; the p.Ap exchange moves
@@ -760,20 +772,23 @@ __device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsig
     const int G = gridDim.x, t = threadIdx.x;
     if (t == 0) *s_bcast = my_partial_t0; // block_sum() left the CTA partial in thread 0 only
     __syncthreads();
+    // Stores and polls are issued by DIFFERENT warps (threads 0..G-1 store, threads kPollBase..kPollBase+G-1 poll):
+    // a strong load queued behind the same thread's strong store waited ~2500 cycles for it (measured).
+    constexpr int kPollBase = 256;
     if (t < G) {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(*s_bcast);
-        unsigned long long *dst = inbox + ((size_t)t * G + blockIdx.x) * 2;
-        // release: ONE fence, then relaxed stores (st.release would fence once per word);
-        // acquire: relaxed polling loads, then ONE fence after the loop
+        unsigned long long *dst = inbox + ((size_t)t * G + blockIdx.x) * kLLStride;
+        // release: ONE fence, then a relaxed store (st.release would fence again)
         if (kPublishes) __threadfence();
-        st_relaxed_gpu_u64(dst + 0, ((unsigned long long)tag << 32) | (bits >> 32));
-        st_relaxed_gpu_u64(dst + 1, ((unsigned long long)tag << 32) | (bits & 0xffffffffull));
-        const unsigned long long *src = inbox + ((size_t)blockIdx.x * G + t) * 2;
+        st_relaxed_gpu_v2u64(dst, ((unsigned long long)tag << 32) | (bits >> 32), ((unsigned long long)tag << 32) | (bits & 0xffffffffull));
+    }
+    if (t >= kPollBase && t < kPollBase + G) {
+        const int srcid = t - kPollBase;
+        const unsigned long long *src = inbox + ((size_t)blockIdx.x * G + srcid) * kLLStride;
         unsigned long long w0, w1;
         const long long t0 = clock64();
         for (;;) {
-            w0 = ld_relaxed_gpu_u64(src + 0);
-            w1 = ld_relaxed_gpu_u64(src + 1);
+            ld_relaxed_gpu_v2u64(src, w0, w1); // each 8-byte half carries its own tag, so a torn 16-byte access is harmless
             if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag) break;
             if (clock64() - t0 > 4000000000LL) {
                 *err_flag = 3;
@@ -781,8 +796,8 @@ __device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsig
                 __trap();
             }
         }
-        if (kPublishes) __threadfence();
-        s_gather[t] = __longlong_as_double((long long)(((w0 & 0xffffffffull) << 32) | (w1 & 0xffffffffull)));
+        if (kPublishes) __threadfence(); // acquire: relaxed polling loads, then ONE fence
+        s_gather[srcid] = __longlong_as_double((long long)(((w0 & 0xffffffffull) << 32) | (w1 & 0xffffffffull)));
     }
     __syncthreads();
     // fixed-order sum by warp 0; the result is returned in ALL LANES OF WARP 0 ONLY (0.0 elsewhere): the caller
@@ -796,16 +811,7 @@ __device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsig
     return s;
 }
 
-constexpr int kPersistThreads = 1024;
-
-// CTA partial of the row owners' contributions (threads 0..rows-1), valid in thread 0.  With at most 32
-// rows per CTA (n <= 32 * grid, the whole latency regime) only warp 0 holds non-zero terms, so one
-// shuffle reduction does it with no shared memory and no CTA barrier; otherwise the general block sum.
-__device__ __forceinline__ double persist_cta_sum(double contrib, bool single_warp, double *scratch)
-{
-    if (single_warp) return threadIdx.x < 32 ? warp_sum(contrib) : 0.0;
-    return block_sum(contrib, scratch);
-}
+constexpr int kPersistThreads = 512; // 128 registers per thread: the exchange and the GEMV stay spill-free
 
 __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(PersistArgs a)
 {
@@ -901,10 +907,13 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
             Ap_own = sum;
             contrib = __dmul_rn(p[r0 + tid], sum);
         }
-        const double cta_pap = persist_cta_sum(contrib, a.rows_max <= 32, scratch);
+        {
+            // with <= 32 rows per CTA the partial lives in warp 0: one shuffle reduction, no CTA barrier
+            const double cta_pap = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
+            const double pAp_w0 = grid_allgather_sum<false>(cta_pap, a.ll, (unsigned int)it, s_gather, &s_bcast, &st->error);
+            if (tid == 0) s_scal[0] = rr / pAp_w0; // alpha = rr / (p.Ap)
+        }
         LAMCG_PHASE(2)
-        const double pAp_w0 = grid_allgather_sum<false>(cta_pap, a.ll, (unsigned int)it, s_gather, &s_bcast, &st->error);
-        if (tid == 0) s_scal[0] = rr / pAp_w0; // alpha = rr / (p.Ap)
         __syncthreads();
         const double alpha = s_scal[0];
         LAMCG_PHASE(3)
@@ -915,9 +924,9 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
             __stcg(&a.r[r0 + tid], r_own);
             contrib = __dmul_rn(r_own, r_own);
         }
-        const double cta_rr = persist_cta_sum(contrib, a.rows_max <= 32, scratch);
+        const double cta_rr = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
+        const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)kLLStride * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
         LAMCG_PHASE(4)
-        const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)2 * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
         if (tid == 0) {
             const double rel0 = sqrt(rrn_w0 / bb);
             s_scal[1] = rrn_w0 / rr; // beta = rr_new / rr
@@ -944,6 +953,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
         st->eps = a.eps;
         st->done = 1;
         for (int k = 0; k < 6; ++k) st->phase_cycles[k] = ph[k];
+
     }
 #undef LAMCG_PHASE
 }

@@ -146,7 +146,8 @@ int lamcg_gemv(lamcg_t *h, const double *p, double *y_local, double *p_dot_y);
  * device milliseconds per launch (CUDA events on that stream), after `warmup` untimed launches. */
 int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch);
 /* Persistent loop only: SM cycles CTA 0 spent in each phase of the last solve, summed over its iterations
- * [0] p update  [1] GEMV  [2] row sums  [3] p.Ap exchange  [4] x/r update  [5] r.r exchange.  Returns the count. */
+ * [0] p update  [1] GEMV  [2] row sums + p.Ap exchange  [3] alpha broadcast  [4] x/r update + r.r exchange
+ * [5] beta broadcast.  Returns the count. */
 int lamcg_get_loop_profile(lamcg_t *h, long long *cycles_out, int capacity);
 /* Plain streaming read of this rank's block (sum of all elements): the read-only HBM ceiling the
  * GEMV is compared with.  Returns average ms per pass and the checksum. */
