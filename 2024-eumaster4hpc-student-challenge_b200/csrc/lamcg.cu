@@ -570,7 +570,8 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->nranks = nranks;
     auto bail = [&](const char *what, cudaError_t err) {
         g_create_error = std::string(what) + ": " + cudaGetErrorString(err);
-        delete h;
+        cudaGetLastError();
+        lamcg_destroy(h); // releases whatever was created so far
         return (int)LAMCG_ERR_CUDA;
     };
     if ((e = cudaSetDevice(device)) != cudaSuccess) return bail("cudaSetDevice", e);
