@@ -37,14 +37,15 @@ enum class Report {
 
 template <typename FloatingType>
 class ConjugateGradient_B200 : public ConjugateGradient<FloatingType> {
-    static_assert(std::is_same<FloatingType, double>::value,
-                  "the B200 hot path is fp64 (the reference drivers instantiate <double>); fp32 is a later row");
+    static_assert(std::is_same<FloatingType, double>::value || std::is_same<FloatingType, float>::value,
+                  "instantiated for double (the hot path) and float, like the reference's GPU classes");
+    static constexpr int kDtype = std::is_same<FloatingType, double>::value ? 0 : 1;
 
 public:
     explicit ConjugateGradient_B200(int device = 0, int rank = 0, int nranks = 1, Report report = Report::Text)
         : rank_(rank), nranks_(nranks), report_(report)
     {
-        const int rc = lamcg_create_ranked(&h_, device, rank, nranks);
+        const int rc = lamcg_create_typed(&h_, device, rank, nranks, kDtype);
         if (rc != LAMCG_OK) {
             std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
             h_ = nullptr;
@@ -84,7 +85,7 @@ public:
                 if (rank_ == 0) std::fprintf(stderr, "peer exchange unavailable (%s); using NCCL\n", lamcg_last_error(h_));
                 lamcg_destroy(h_);
                 h_ = nullptr;
-                if (lamcg_create_ranked(&h_, i.device, rank_, nranks_) != LAMCG_OK) return 0.0;
+                if (lamcg_create_typed(&h_, i.device, rank_, nranks_, kDtype) != LAMCG_OK) return 0.0;
             }
         }
         if (!peer) {

@@ -54,7 +54,7 @@ class lamcg_info(ctypes.Structure):
                 ("lda", ctypes.c_size_t), ("rank", ctypes.c_int), ("nranks", ctypes.c_int), ("device", ctypes.c_int),
                 ("sm_count", ctypes.c_int), ("comm_mode", ctypes.c_int), ("has_matrix", ctypes.c_int),
                 ("has_rhs", ctypes.c_int), ("gemv_variant", ctypes.c_int), ("gemv_grid", ctypes.c_int),
-                ("gemv_block", ctypes.c_int), ("gemv_smem_bytes", ctypes.c_int)]
+                ("gemv_block", ctypes.c_int), ("gemv_smem_bytes", ctypes.c_int), ("dtype", ctypes.c_int)]
 
 
 def build(verbose: bool = False) -> str:
@@ -74,6 +74,7 @@ _vp, _cp, _dp = ctypes.c_void_p, ctypes.c_char_p, ctypes.POINTER(ctypes.c_double
 _SIGNATURES = {
     "lamcg_create": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int]),
     "lamcg_create_ranked": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "lamcg_create_typed": (ctypes.c_int, [ctypes.POINTER(_vp), ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "lamcg_destroy": (None, [_vp]),
     "lamcg_last_error": (_cp, [_vp]),
     "lamcg_version": (_cp, []),
@@ -93,10 +94,10 @@ _SIGNATURES = {
     "lamcg_save_system": (ctypes.c_int, [_vp, _cp, _cp]),
     "lamcg_solve": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.POINTER(lamcg_result)]),
     "lamcg_get_residual_history": (ctypes.c_int, [_vp, _dp, ctypes.c_int]),
-    "lamcg_get_solution_local": (ctypes.c_int, [_vp, _dp]),
-    "lamcg_get_solution": (ctypes.c_int, [_vp, _dp]),
+    "lamcg_get_solution_local": (ctypes.c_int, [_vp, _vp]),
+    "lamcg_get_solution": (ctypes.c_int, [_vp, _vp]),
     "lamcg_save_solution": (ctypes.c_int, [_vp, _cp]),
-    "lamcg_gemv": (ctypes.c_int, [_vp, _dp, _dp, _dp]),
+    "lamcg_gemv": (ctypes.c_int, [_vp, _vp, _vp, _dp]),
     "lamcg_time_gemv": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp]),
     "lamcg_get_loop_profile": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
     "lamcg_time_stream_read": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp, _dp]),
@@ -119,20 +120,24 @@ def lib() -> ctypes.CDLL:
     return _lib
 
 
-def _as_f64(a, name: str) -> np.ndarray:
-    arr = np.ascontiguousarray(a, dtype=np.float64)
+def _as_array(a, name: str, dtype=np.float64) -> np.ndarray:
+    arr = np.ascontiguousarray(a, dtype=dtype)
     if arr.size == 0:
         raise ValueError(f"{name} is empty")
     return arr
 
 
+DTYPES = {"f64": (0, np.float64), "f32": (1, np.float32), np.float64: (0, np.float64), np.float32: (1, np.float32)}
+
+
 class Solver:
     """Direct, exception-raising wrapper over one ``lamcg_t`` (one rank == one GPU)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1):
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, dtype="f64"):
         self._L = lib()
         h = _vp()
-        rc = self._L.lamcg_create_ranked(ctypes.byref(h), device, rank, nranks)
+        self.dtype_code, self.np_dtype = DTYPES[dtype]
+        rc = self._L.lamcg_create_typed(ctypes.byref(h), device, rank, nranks, self.dtype_code)
         if rc != 0:
             raise LamcgError(rc, (self._L.lamcg_last_error(None) or b"").decode())
         self._h = h
@@ -210,21 +215,21 @@ class Solver:
     def set_matrix(self, A, layout: int = 0) -> None:
         """A: numpy array (host) or an object with ``data_ptr()`` (torch tensor, host or device)."""
         if hasattr(A, "data_ptr"):
-            assert A.is_contiguous() and A.element_size() == 8
+            assert A.is_contiguous() and A.element_size() == np.dtype(self.np_dtype).itemsize
             n = A.shape[1]
             self._keep_A = A
             self._ck(self._L.lamcg_set_matrix(self._h, _vp(A.data_ptr()), n, layout))
         else:
-            arr = _as_f64(A, "A")
+            arr = _as_array(A, "A", self.np_dtype)
             assert arr.ndim == 2
             self._ck(self._L.lamcg_set_matrix(self._h, _vp(arr.ctypes.data), arr.shape[1], layout))
 
     def set_rhs(self, b) -> None:
         if hasattr(b, "data_ptr"):
-            assert b.is_contiguous() and b.element_size() == 8
+            assert b.is_contiguous() and b.element_size() == np.dtype(self.np_dtype).itemsize
             self._ck(self._L.lamcg_set_rhs(self._h, _vp(b.data_ptr()), b.numel()))
         else:
-            arr = _as_f64(b, "b").reshape(-1)
+            arr = _as_array(b, "b", self.np_dtype).reshape(-1)
             self._ck(self._L.lamcg_set_rhs(self._h, _vp(arr.ctypes.data), arr.size))
 
     def random_spd_system(self, n: int, seed: int) -> None:
@@ -247,17 +252,17 @@ class Solver:
         return buf[:cnt].copy()
 
     def solution_local(self) -> np.ndarray:
-        x = np.zeros(max(self.info.local_rows, 1))
-        self._ck(self._L.lamcg_get_solution_local(self._h, x.ctypes.data_as(_dp)))
+        x = np.zeros(max(self.info.local_rows, 1), dtype=self.np_dtype)
+        self._ck(self._L.lamcg_get_solution_local(self._h, _vp(x.ctypes.data)))
         return x[: self.info.local_rows]
 
     def solution(self, out=None) -> np.ndarray:
         """Whole x; ``out`` may be a pinned torch tensor / numpy array of n doubles."""
         n = self.info.n
         if out is None:
-            out = np.zeros(n)
+            out = np.zeros(n, dtype=self.np_dtype)
         ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
-        self._ck(self._L.lamcg_get_solution(self._h, ctypes.cast(_vp(ptr), _dp)))
+        self._ck(self._L.lamcg_get_solution(self._h, _vp(ptr)))
         return out
 
     def save_solution(self, path: str) -> None:
@@ -265,10 +270,10 @@ class Solver:
 
     # -- hooks
     def gemv(self, p) -> tuple[np.ndarray, float]:
-        p = _as_f64(p, "p").reshape(-1)
-        y = np.zeros(max(self.info.local_rows, 1))
+        p = _as_array(p, "p", self.np_dtype).reshape(-1)
+        y = np.zeros(max(self.info.local_rows, 1), dtype=self.np_dtype)
         d = ctypes.c_double()
-        self._ck(self._L.lamcg_gemv(self._h, p.ctypes.data_as(_dp), y.ctypes.data_as(_dp), ctypes.byref(d)))
+        self._ck(self._L.lamcg_gemv(self._h, _vp(p.ctypes.data), _vp(y.ctypes.data), ctypes.byref(d)))
         return y[: self.info.local_rows], d.value
 
     def time_gemv(self, warmup: int = 3, reps: int = 10) -> float:
@@ -295,8 +300,8 @@ class ConjugateGradient_B200:
 
     Same public methods as LAM::ConjugateGradient_CPU_MPI_OMP<double> (MPI_OMP.hpp:22-35)."""
 
-    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, verbose: bool = True):
-        self._s = Solver(device, rank, nranks)
+    def __init__(self, device: int = 0, rank: int = 0, nranks: int = 1, verbose: bool = True, dtype="f64"):
+        self._s = Solver(device, rank, nranks, dtype)
         self.verbose = verbose
         self.last_result: lamcg_result | None = None
 

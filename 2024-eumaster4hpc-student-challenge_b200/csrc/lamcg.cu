@@ -60,8 +60,11 @@ struct lamcg {
     cudaStream_t stream = nullptr;
     size_t n = 0, local_rows = 0, row_offset = 0, lda = 0;
     size_t alloc_n = 0;
-    double *A = nullptr, *b_full = nullptr, *x = nullptr, *r = nullptr, *Ap = nullptr, *p_full = nullptr;
-    double *x_full = nullptr; // gather target for get_solution (multi-rank), [lda]
+    int dtype = 0;                 // 0 = fp64 (the hot path), 1 = fp32 storage (reductions and scalars stay fp64)
+    size_t esz = sizeof(double);   // bytes per stored element
+    // byte pointers: element type is `dtype`
+    char *A = nullptr, *b_full = nullptr, *x = nullptr, *r = nullptr, *Ap = nullptr, *p_full = nullptr;
+    char *x_full = nullptr; // gather target for get_solution (multi-rank), [lda]
     double *partials = nullptr; // [2 * kMaxGrid]
     double *hist = nullptr;
     int hist_cap = 0;
@@ -147,7 +150,8 @@ template <int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0>
 bool plan_ctarow(lamcg *h, GemvPlan &p, int variant)
 {
     p.variant = variant;
-    p.kernel = gemv_ctarow_kernel<R, U, NT, CPS, PF>;
+    if (h->dtype == 0) p.kernel = gemv_ctarow_kernel<double, R, U, NT, CPS, PF>;
+    else p.kernel = gemv_ctarow_kernel<float, R, U, NT, CPS, 0>;
     p.block = NT;
     p.smem = 0;
     p.rows_per_pass = R;
@@ -179,6 +183,8 @@ int make_plan(lamcg *h)
     // flight is the fastest on tall blocks (7.3-7.4 TB/s at 100000 and 12500 rows); on short blocks the
     // 256-thread, 2 CTA/SM shape balances better (6.5-6.7 TB/s at 10000 rows)
     if (v == 0) v = h->local_rows >= 12000 ? 36 : 32;
+    if (h->dtype != 0 && (v < 30 || v > 39) && v != 61 && v != 62 && v != 63 && v != 65 && v != 67 && v != 68 && v != 69 && v != 70)
+        return h->fail(LAMCG_ERR_INVALID, "gemv_variant %d is fp64 only (fp32 handles use the cta-rows family 30-39, 6x)", v);
     bool ok = false;
     GemvPlan p;
     switch (v) {
@@ -263,30 +269,30 @@ int alloc_system(lamcg *h, size_t n)
     partition(n, h->nranks, h->rank, &h->local_rows, &h->row_offset);
     h->lda = (n + 15) / 16 * 16; // rows start on 128-byte boundaries; pad columns are zero
     const size_t rows_alloc = std::max<size_t>(h->local_rows, 1);
-    cudaError_t e = cudaMalloc(&h->A, rows_alloc * h->lda * sizeof(double));
+    cudaError_t e = cudaMalloc(&h->A, rows_alloc * h->lda * h->esz);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return h->fail(LAMCG_ERR_NOMEM, "cudaMalloc of the %zu x %zu row block (%.2f GB) failed: %s", h->local_rows, h->lda,
-                       rows_alloc * h->lda * 8.0 / 1e9, cudaGetErrorString(e));
+                       rows_alloc * h->lda * (double)h->esz / 1e9, cudaGetErrorString(e));
     }
-    CK(cudaMalloc(&h->b_full, h->lda * sizeof(double)));
-    CK(cudaMalloc(&h->p_full, h->lda * sizeof(double)));
-    CK(cudaMalloc(&h->x_full, h->lda * sizeof(double)));
-    CK(cudaMalloc(&h->x, rows_alloc * sizeof(double)));
-    CK(cudaMalloc(&h->r, rows_alloc * sizeof(double)));
-    CK(cudaMalloc(&h->Ap, rows_alloc * sizeof(double)));
-    CK(cudaMemsetAsync(h->b_full, 0, h->lda * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->p_full, 0, h->lda * sizeof(double), h->stream));
-    CK(cudaMemsetAsync(h->x, 0, rows_alloc * sizeof(double), h->stream));
+    CK(cudaMalloc(&h->b_full, h->lda * h->esz));
+    CK(cudaMalloc(&h->p_full, h->lda * h->esz));
+    CK(cudaMalloc(&h->x_full, h->lda * h->esz));
+    CK(cudaMalloc(&h->x, rows_alloc * h->esz));
+    CK(cudaMalloc(&h->r, rows_alloc * h->esz));
+    CK(cudaMalloc(&h->Ap, rows_alloc * h->esz));
+    CK(cudaMemsetAsync(h->b_full, 0, h->lda * h->esz, h->stream));
+    CK(cudaMemsetAsync(h->p_full, 0, h->lda * h->esz, h->stream));
+    CK(cudaMemsetAsync(h->x, 0, rows_alloc * h->esz, h->stream));
     h->alloc_n = n;
     int rc = make_plan(h);
     if (rc != LAMCG_OK) return rc;
     return LAMCG_OK;
 }
 
-double *p_ptr(lamcg *h, int par)
+char *p_ptr(lamcg *h, int par)
 {
-    if (h->comm_mode == kCommPeer) return reinterpret_cast<double *>(h->peer_base + h->pv.off_p[par & 1]);
+    if (h->comm_mode == kCommPeer) return reinterpret_cast<char *>(h->peer_base + h->pv.off_p[par & 1]);
     return h->p_full;
 }
 
@@ -351,15 +357,16 @@ VecArgs vec_args(lamcg *h, int par)
 
 // All-gather of the p slices with the reference partition: P equal slices of n/P plus the
 // remainder owned by the last rank (MPI_OMP.hpp:505 gathers Ap the same way with Allgatherv).
-int allgather_vec(lamcg *h, double *full)
+int allgather_vec(lamcg *h, char *full)
 {
     NcclApi &N = nccl_api();
+    const ncclDataType_t dt = h->dtype == 0 ? ncclDouble : ncclFloat;
     const size_t base = h->n / (size_t)h->nranks;
     const size_t tail = h->n % (size_t)h->nranks;
-    if (base > 0) NCK(N.AllGather(full + h->row_offset, full, base, ncclDouble, h->nccl, h->stream));
+    if (base > 0) NCK(N.AllGather(full + h->row_offset * h->esz, full, base, dt, h->nccl, h->stream));
     if (tail > 0) {
-        double *t = full + base * (size_t)h->nranks;
-        NCK(N.Broadcast(t, t, tail, ncclDouble, h->nranks - 1, h->nccl, h->stream));
+        char *t = full + base * (size_t)h->nranks * h->esz;
+        NCK(N.Broadcast(t, t, tail, dt, h->nranks - 1, h->nccl, h->stream));
     }
     return LAMCG_OK;
 }
@@ -376,11 +383,13 @@ int enqueue_iteration(lamcg *h, int par, cudaEvent_t ev0, cudaEvent_t ev1, int *
         NCK(N.AllReduce(&h->st->pAp_local, &h->st->pAp, 1, ncclDouble, ncclSum, h->nccl, h->stream));
     VecArgs v = vec_args(h, par);
     const int vg = vec_grid(h);
-    update_xr_kernel<<<vg, kVecThreads, 0, h->stream>>>(v);
+    if (h->dtype == 0) update_xr_kernel<double><<<vg, kVecThreads, 0, h->stream>>>(v);
+    else update_xr_kernel<float><<<vg, kVecThreads, 0, h->stream>>>(v);
     CK(cudaGetLastError());
     if (h->comm_mode == kCommNccl)
         NCK(N.AllReduce(&h->st->rrn_local, &h->st->rrn, 1, ncclDouble, ncclSum, h->nccl, h->stream));
-    update_p_kernel<<<vg, kVecThreads, 0, h->stream>>>(v);
+    if (h->dtype == 0) update_p_kernel<double><<<vg, kVecThreads, 0, h->stream>>>(v);
+    else update_p_kernel<float><<<vg, kVecThreads, 0, h->stream>>>(v);
     CK(cudaGetLastError());
     if (h->comm_mode == kCommNccl) {
         rc = allgather_vec(h, h->p_full);
@@ -437,6 +446,7 @@ int check_device_error(lamcg *h, const DevState &s)
 int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *out)
 {
     if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "the persistent loop is single-rank");
+    if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "the persistent loop is fp64 only");
     if (h->n > kPersistMaxN) return h->fail(LAMCG_ERR_INVALID, "the persistent loop supports n <= %zu", kPersistMaxN);
 
     const int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
@@ -463,10 +473,10 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     if (max_blocks < 1) return h->fail(LAMCG_ERR_CUDA, "persistent kernel does not fit on an SM (smem %zu)", smem);
 
     PersistArgs a;
-    a.A = h->A;
-    a.b = h->b_full;
-    a.x = h->x;
-    a.r = h->r;
+    a.A = reinterpret_cast<const double *>(h->A);
+    a.b = reinterpret_cast<const double *>(h->b_full);
+    a.x = reinterpret_cast<double *>(h->x);
+    a.r = reinterpret_cast<double *>(h->r);
     a.hist = h->opt_history ? h->hist : nullptr;
     a.ll = h->persist_ll;
     a.st = h->st;
@@ -606,6 +616,20 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
 
 int lamcg_create(lamcg_t **out, int device) { return lamcg_create_ranked(out, device, 0, 1); }
 
+int lamcg_create_typed(lamcg_t **out, int device, int rank, int nranks, int dtype)
+{
+    if (dtype != 0 && dtype != 1) {
+        g_create_error = "dtype must be 0 (fp64) or 1 (fp32)";
+        if (out) *out = nullptr;
+        return LAMCG_ERR_INVALID;
+    }
+    int rc = lamcg_create_ranked(out, device, rank, nranks);
+    if (rc != LAMCG_OK) return rc;
+    (*out)->dtype = dtype;
+    (*out)->esz = dtype == 0 ? sizeof(double) : sizeof(float);
+    return LAMCG_OK;
+}
+
 void lamcg_destroy(lamcg_t *h)
 {
     if (!h) return;
@@ -673,6 +697,7 @@ int lamcg_get_info(const lamcg_t *h, lamcg_info *out)
     out->gemv_grid = h->plan.grid;
     out->gemv_block = h->plan.block;
     out->gemv_smem_bytes = (int)h->plan.smem;
+    out->dtype = h->dtype;
     return LAMCG_OK;
 }
 
@@ -729,7 +754,7 @@ int lamcg_comm_peer_export(lamcg_t *h, size_t n, void *handle_out)
     const size_t hdr = (sizeof(PeerHeader) + 255) / 256 * 256;
     h->pv = PeerView{};
     h->pv.off_p[0] = (long long)hdr;
-    h->pv.off_p[1] = (long long)(hdr + lda * 8);
+    h->pv.off_p[1] = (long long)(hdr + lda * 8);   // sized for fp64; fp32 handles use the first half of each buffer
     h->pv.off_xg[0] = (long long)(hdr + 2 * lda * 8);
     h->pv.off_xg[1] = (long long)(hdr + 3 * lda * 8);
     h->peer_bytes = hdr + 4 * lda * 8;
@@ -790,8 +815,12 @@ int lamcg_generate_matrix(lamcg_t *h, size_t rows, size_t cols)
     if (h->local_rows > 0) {
         const long long total = (long long)h->local_rows * (long long)(h->lda / 2);
         const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
-        generate_matrix_kernel<<<grid, 256, 0, h->stream>>>(h->A, (long long)h->local_rows, (long long)h->n, (long long)h->lda,
-                                                           (long long)h->row_offset);
+        if (h->dtype == 0)
+            generate_matrix_kernel<double><<<grid, 256, 0, h->stream>>>(h->A, (long long)h->local_rows, (long long)h->n, (long long)h->lda,
+                                                                       (long long)h->row_offset);
+        else
+            generate_matrix_kernel<float><<<grid, 256, 0, h->stream>>>(h->A, (long long)h->local_rows, (long long)h->n, (long long)h->lda,
+                                                                      (long long)h->row_offset);
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(h->stream));
@@ -806,36 +835,36 @@ int lamcg_generate_rhs(lamcg_t *h)
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "generate_rhs before a matrix exists");
     CK(cudaSetDevice(h->device));
     const int grid = (int)std::min<size_t>((h->lda + 255) / 256, (size_t)h->sm_count * 4);
-    fill_kernel<<<grid, 256, 0, h->stream>>>(h->b_full, (long long)h->n, (long long)h->lda, 1.0);
+    if (h->dtype == 0) fill_kernel<double><<<grid, 256, 0, h->stream>>>(h->b_full, (long long)h->n, (long long)h->lda, 1.0);
+    else fill_kernel<float><<<grid, 256, 0, h->stream>>>(h->b_full, (long long)h->n, (long long)h->lda, 1.0);
     CK(cudaGetLastError());
     CK(cudaStreamSynchronize(h->stream));
     h->has_rhs = true;
     return LAMCG_OK;
 }
 
-int lamcg_set_matrix(lamcg_t *h, const double *A, size_t n, int layout)
+int lamcg_set_matrix(lamcg_t *h, const void *A, size_t n, int layout)
 {
     if (!h || !A) return LAMCG_ERR_INVALID;
     int rc = alloc_system(h, n);
     if (rc != LAMCG_OK) return rc;
-    const double *src = layout == 0 ? A + h->row_offset * n : A;
-    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * sizeof(double), h->stream));
+    const char *src = layout == 0 ? static_cast<const char *>(A) + h->row_offset * n * h->esz : static_cast<const char *>(A);
+    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * h->esz, h->stream));
     if (h->local_rows > 0)
-        CK(cudaMemcpy2DAsync(h->A, h->lda * sizeof(double), src, n * sizeof(double), n * sizeof(double), h->local_rows,
-                             cudaMemcpyDefault, h->stream));
+        CK(cudaMemcpy2DAsync(h->A, h->lda * h->esz, src, n * h->esz, n * h->esz, h->local_rows, cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->has_matrix = true;
     h->has_rhs = false;
     return LAMCG_OK;
 }
 
-int lamcg_set_rhs(lamcg_t *h, const double *b, size_t n)
+int lamcg_set_rhs(lamcg_t *h, const void *b, size_t n)
 {
     if (!h || !b) return LAMCG_ERR_INVALID;
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "set_rhs before a matrix exists");
     if (n != h->n) return h->fail(LAMCG_ERR_SHAPE, "Size of right hand side does not match the matrix");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemcpyAsync(h->b_full, b, n * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaMemcpyAsync(h->b_full, b, n * h->esz, cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->has_rhs = true;
     return LAMCG_OK;
@@ -851,7 +880,7 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
     if (rc != LAMCG_OK) { close(fd); return rc; }
     if (rows != cols) { close(fd); return h->fail(LAMCG_ERR_SHAPE, "Matrix has to be square"); }
     struct stat sb;
-    if (fstat(fd, &sb) == 0 && (unsigned long long)sb.st_size < 16ull + (unsigned long long)rows * cols * 8ull) {
+    if (fstat(fd, &sb) == 0 && (unsigned long long)sb.st_size < 16ull + (unsigned long long)rows * cols * (unsigned long long)h->esz) {
         close(fd);
         return h->fail(LAMCG_ERR_IO, "%s: file is shorter than its %zu x %zu header promises", path, rows, cols);
     }
@@ -863,13 +892,13 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
     // async 2-D H2D copy of chunk k.  One thread tops out near 6 GB/s (a single core's memcpy rate out of the
     // page cache, the same rate the reference's fread reaches into pageable memory); T threads scale that
     // until PCIe is the limit.
-    const size_t row_bytes = n * sizeof(double);
+    const size_t row_bytes = n * h->esz; // file elements have the handle's type, like the reference's sizeof(FloatingType)
     size_t chunk_rows = std::max<size_t>(1, (size_t)(32u << 20) / row_bytes);
     chunk_rows = std::min(chunk_rows, std::max<size_t>(h->local_rows, 1));
     const size_t nchunks = (h->local_rows + chunk_rows - 1) / chunk_rows;
     int T = (int)std::max<long long>(1, std::min<long long>(h->opt_ingest_threads, 16));
     T = (int)std::min<size_t>((size_t)T, std::max<size_t>(nchunks, 1));
-    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * sizeof(double), h->stream));
+    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * h->esz, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     std::atomic<int> status{LAMCG_OK};
     std::string first_error;
@@ -881,7 +910,7 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
         };
         if (cudaSetDevice(h->device) != cudaSuccess) return failw(LAMCG_ERR_CUDA, "cudaSetDevice failed in ingest thread");
         cudaStream_t st = nullptr;
-        double *stage[2] = {nullptr, nullptr};
+        char *stage[2] = {nullptr, nullptr};
         cudaEvent_t done[2] = {nullptr, nullptr};
         bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
         for (int i = 0; i < 2 && ok; ++i)
@@ -899,7 +928,7 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
                                         std::to_string(h->row_offset + r + nr));
                 break;
             }
-            cudaError_t e = cudaMemcpy2DAsync(h->A + r * h->lda, h->lda * sizeof(double), stage[slot], row_bytes, row_bytes, nr,
+            cudaError_t e = cudaMemcpy2DAsync(h->A + r * h->lda * h->esz, h->lda * h->esz, stage[slot], row_bytes, row_bytes, nr,
                                               cudaMemcpyHostToDevice, st);
             if (e != cudaSuccess) { failw(LAMCG_ERR_CUDA, std::string("cudaMemcpy2DAsync failed: ") + cudaGetErrorString(e)); break; }
             cudaEventRecord(done[slot], st);
@@ -935,8 +964,8 @@ int lamcg_load_rhs(lamcg_t *h, const char *path)
     if (rc != LAMCG_OK) { close(fd); return rc; }
     if (cols != 1) { close(fd); return h->fail(LAMCG_ERR_SHAPE, "The file does not contain a valid rhs"); }
     if (rows != h->n) { close(fd); return h->fail(LAMCG_ERR_SHAPE, "Size of right hand side does not match the matrix"); }
-    std::vector<double> b(rows);
-    if (pread_full(fd, b.data(), rows * sizeof(double), 16) != 0) {
+    std::vector<char> b(rows * h->esz);
+    if (pread_full(fd, b.data(), rows * h->esz, 16) != 0) {
         close(fd);
         return h->fail(LAMCG_ERR_IO, "%s: short read", path);
     }
@@ -957,7 +986,7 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     int loop_mode = (int)h->opt_loop_mode;
     if (loop_mode == kLoopAuto) {
         if (h->opt_time_gemv) loop_mode = kLoopStream;
-        else if (h->nranks == 1 && h->n <= kPersistAutoMaxN) loop_mode = kLoopPersistent;
+        else if (h->nranks == 1 && h->dtype == 0 && h->n <= kPersistAutoMaxN) loop_mode = kLoopPersistent;
         else loop_mode = kLoopGraph;
     }
     if (h->opt_time_gemv) loop_mode = kLoopStream;
@@ -994,7 +1023,8 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     ia.eps = rel_error;
     ia.max_iters = max_iters;
     ia.hist_cap = h->opt_history ? h->hist_cap : 0;
-    init_solve_kernel<<<1, 1024, 0, h->stream>>>(ia);
+    if (h->dtype == 0) init_solve_kernel<double><<<1, 1024, 0, h->stream>>>(ia);
+    else init_solve_kernel<float><<<1, 1024, 0, h->stream>>>(ia);
     CK(cudaGetLastError());
     int launches = 1;
 
@@ -1072,17 +1102,17 @@ int lamcg_get_residual_history(lamcg_t *h, double *out, int capacity)
     return cnt;
 }
 
-int lamcg_get_solution_local(lamcg_t *h, double *x_local)
+int lamcg_get_solution_local(lamcg_t *h, void *x_local)
 {
     if (!h || !x_local) return LAMCG_ERR_INVALID;
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no system");
     CK(cudaSetDevice(h->device));
-    if (h->local_rows) CK(cudaMemcpyAsync(x_local, h->x, h->local_rows * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->local_rows) CK(cudaMemcpyAsync(x_local, h->x, h->local_rows * h->esz, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return LAMCG_OK;
 }
 
-int lamcg_get_solution(lamcg_t *h, double *x)
+int lamcg_get_solution(lamcg_t *h, void *x)
 {
     if (!h || !x) return LAMCG_ERR_INVALID;
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no system");
@@ -1091,22 +1121,26 @@ int lamcg_get_solution(lamcg_t *h, double *x)
     if (h->comm_mode == kCommPeer) {
         const unsigned long long gseq = ++h->gather_seq;
         const int buf = (int)(gseq & 1ull);
-        peer_gather_put_kernel<<<vec_grid(h), kVecThreads, 0, h->stream>>>(h->pv, h->x, (long long)h->local_rows, (long long)h->row_offset,
-                                                                          buf, gseq, h->st);
+        if (h->dtype == 0)
+            peer_gather_put_kernel<double><<<vec_grid(h), kVecThreads, 0, h->stream>>>(h->pv, h->x, (long long)h->local_rows,
+                                                                                      (long long)h->row_offset, buf, gseq, h->st);
+        else
+            peer_gather_put_kernel<float><<<vec_grid(h), kVecThreads, 0, h->stream>>>(h->pv, h->x, (long long)h->local_rows,
+                                                                                     (long long)h->row_offset, buf, gseq, h->st);
         CK(cudaGetLastError());
         peer_gather_wait_kernel<<<1, 32, 0, h->stream>>>(h->pv, gseq, h->st);
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(x, h->peer_base + h->pv.off_xg[buf], h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(x, h->peer_base + h->pv.off_xg[buf], h->n * h->esz, cudaMemcpyDeviceToHost, h->stream));
         cudaError_t se = cudaStreamSynchronize(h->stream);
         if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "solution gather faulted on the device: %s", cudaGetErrorString(se));
         return LAMCG_OK;
     }
     if (h->comm_mode != kCommNccl) return h->fail(LAMCG_ERR_STATE, "get_solution over ranks needs an initialised communicator");
     if (h->local_rows)
-        CK(cudaMemcpyAsync(h->x_full + h->row_offset, h->x, h->local_rows * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->x_full + h->row_offset * h->esz, h->x, h->local_rows * h->esz, cudaMemcpyDeviceToDevice, h->stream));
     int rc = allgather_vec(h, h->x_full);
     if (rc != LAMCG_OK) return rc;
-    CK(cudaMemcpyAsync(x, h->x_full, h->n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaMemcpyAsync(x, h->x_full, h->n * h->esz, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     return LAMCG_OK;
 }
@@ -1115,14 +1149,14 @@ int lamcg_save_solution(lamcg_t *h, const char *path)
 {
     if (!h || !path) return LAMCG_ERR_INVALID;
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no system");
-    std::vector<double> x(h->n);
+    std::vector<char> x(h->n * h->esz);
     int rc = lamcg_get_solution(h, x.data());
     if (rc != LAMCG_OK) return rc;
     if (h->rank != 0) return LAMCG_OK; // only rank 0 saves (MPI_OMP.hpp:426)
     FILE *f = fopen(path, "wb");
     if (!f) return h->fail(LAMCG_ERR_IO, "Cannot open output file %s: %s", path, strerror(errno));
     const uint64_t hdr[2] = {(uint64_t)h->n, 1ull};
-    bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1 && fwrite(x.data(), sizeof(double), h->n, f) == h->n;
+    bool ok = fwrite(hdr, sizeof hdr, 1, f) == 1 && fwrite(x.data(), h->esz, h->n, f) == h->n;
     ok = (fclose(f) == 0) && ok;
     if (!ok) return h->fail(LAMCG_ERR_IO, "short write to %s", path);
     return LAMCG_OK;
@@ -1196,6 +1230,7 @@ int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
 {
     if (!h || n == 0) return LAMCG_ERR_INVALID;
     if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "the SPD generator runs on one rank (generate, save, then load row blocks)");
+    if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "the SPD generator is fp64 only");
     int rc = alloc_system(h, n);
     if (rc != LAMCG_OK) return rc;
     double *Q = nullptr, *buf = nullptr, *d_dev = nullptr;
@@ -1232,7 +1267,7 @@ int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
     }
     // A = Y Y^T into the padded row-major block (symmetric, so row-major == the reference's column-major file)
     if (h->lda != n) cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * sizeof(double), h->stream);
-    rc = launch_gemm(h, Q, Q, h->A, (long long)n, (long long)n, (long long)n, /*sai*/ 1, /*sak*/ (long long)n, /*sbk*/ (long long)n,
+    rc = launch_gemm(h, Q, Q, reinterpret_cast<double *>(h->A), (long long)n, (long long)n, (long long)n, /*sai*/ 1, /*sak*/ (long long)n, /*sbk*/ (long long)n,
                      /*sbj*/ 1, /*sci*/ (long long)h->lda, /*scj*/ 1, 1.0, 0.0);
     cudaError_t se = cudaStreamSynchronize(h->stream);
     cleanup();
@@ -1248,6 +1283,7 @@ int lamcg_save_system(lamcg_t *h, const char *matrix_path, const char *rhs_path)
 {
     if (!h || !matrix_path || !rhs_path) return LAMCG_ERR_INVALID;
     if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "save_system runs on one rank");
+    if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "save_system is fp64 only");
     if (!h->has_matrix || !h->has_rhs) return h->fail(LAMCG_ERR_STATE, "no system to save");
     CK(cudaSetDevice(h->device));
     const size_t n = h->n;
@@ -1259,7 +1295,7 @@ int lamcg_save_system(lamcg_t *h, const char *matrix_path, const char *rhs_path)
     std::vector<double> stage(chunk_rows * n);
     for (size_t r = 0; ok && r < n; r += chunk_rows) {
         const size_t nr = std::min(chunk_rows, n - r);
-        cudaError_t e = cudaMemcpy2D(stage.data(), n * sizeof(double), h->A + r * h->lda, h->lda * sizeof(double), n * sizeof(double), nr,
+        cudaError_t e = cudaMemcpy2D(stage.data(), n * sizeof(double), h->A + r * h->lda * sizeof(double), h->lda * sizeof(double), n * sizeof(double), nr,
                                      cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) { fclose(f); return h->fail(LAMCG_ERR_CUDA, "download of the matrix failed: %s", cudaGetErrorString(e)); }
         ok = fwrite(stage.data(), sizeof(double), nr * n, f) == nr * n;
@@ -1277,16 +1313,16 @@ int lamcg_save_system(lamcg_t *h, const char *matrix_path, const char *rhs_path)
 }
 
 // ---- measurement / test hooks ----------------------------------------------------------------
-int lamcg_gemv(lamcg_t *h, const double *p, double *y_local, double *p_dot_y)
+int lamcg_gemv(lamcg_t *h, const void *p, void *y_local, double *p_dot_y)
 {
     if (!h || !p || !y_local) return LAMCG_ERR_INVALID;
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
     CK(cudaSetDevice(h->device));
-    CK(cudaMemsetAsync(p_ptr(h, 0), 0, h->lda * sizeof(double), h->stream));
-    CK(cudaMemcpyAsync(p_ptr(h, 0), p, h->n * sizeof(double), cudaMemcpyDefault, h->stream));
+    CK(cudaMemsetAsync(p_ptr(h, 0), 0, h->lda * h->esz, h->stream));
+    CK(cudaMemcpyAsync(p_ptr(h, 0), p, h->n * h->esz, cudaMemcpyDefault, h->stream));
     int rc = launch_gemv(h, 0);
     if (rc != LAMCG_OK) return rc;
-    if (h->local_rows) CK(cudaMemcpyAsync(y_local, h->Ap, h->local_rows * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (h->local_rows) CK(cudaMemcpyAsync(y_local, h->Ap, h->local_rows * h->esz, cudaMemcpyDeviceToHost, h->stream));
     CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
     cudaError_t se = cudaStreamSynchronize(h->stream);
     if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "GEMV faulted on the device: %s", cudaGetErrorString(se));
@@ -1330,11 +1366,11 @@ int lamcg_time_stream_read(lamcg_t *h, int warmup, int reps, double *ms_per_pass
     if (!h || reps <= 0 || !ms_per_pass) return LAMCG_ERR_INVALID;
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
     CK(cudaSetDevice(h->device));
-    const long long count2 = (long long)(h->local_rows * h->lda / 2);
+    const long long count2 = (long long)(h->local_rows * h->lda * h->esz / 16);
     const int grid = std::min(h->sm_count * 8, kMaxGrid);
-    for (int i = 0; i < warmup; ++i) stream_read_kernel<<<grid, 256, 0, h->stream>>>(h->A, count2, h->partials);
+    for (int i = 0; i < warmup; ++i) stream_read_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double *>(h->A), count2, h->partials);
     CK(cudaEventRecord(h->ev_start, h->stream));
-    for (int i = 0; i < reps; ++i) stream_read_kernel<<<grid, 256, 0, h->stream>>>(h->A, count2, h->partials);
+    for (int i = 0; i < reps; ++i) stream_read_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double *>(h->A), count2, h->partials);
     CK(cudaEventRecord(h->ev_stop, h->stream));
     CK(cudaGetLastError());
     std::vector<double> part(grid);

@@ -68,8 +68,10 @@ struct PeerView {
 };
 
 __device__ __forceinline__ PeerHeader *peer_hdr(const PeerView &pv, int r) { return reinterpret_cast<PeerHeader *>(pv.base[r]); }
-__device__ __forceinline__ double *peer_p(const PeerView &pv, int r, int buf) { return reinterpret_cast<double *>(pv.base[r] + pv.off_p[buf]); }
-__device__ __forceinline__ double *peer_xg(const PeerView &pv, int r, int buf) { return reinterpret_cast<double *>(pv.base[r] + pv.off_xg[buf]); }
+template <typename T = double>
+__device__ __forceinline__ T *peer_p(const PeerView &pv, int r, int buf) { return reinterpret_cast<T *>(pv.base[r] + pv.off_p[buf]); }
+template <typename T = double>
+__device__ __forceinline__ T *peer_xg(const PeerView &pv, int r, int buf) { return reinterpret_cast<T *>(pv.base[r] + pv.off_xg[buf]); }
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
 {
@@ -195,6 +197,57 @@ __device__ __forceinline__ double2 ldg_stream_f64x2_pf256(const double *ptr, uin
                  : "l"(ptr), "l"(policy));
     return v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Element-type helpers.  The hot path is fp64 (what the reference's drivers instantiate); the <float>
+// instantiation of the reference classes is served by the same kernels with T = float for everything that
+// is STORED (A, b, x, r, p, Ap) while every reduction, alpha, beta and the stop test stay in fp64.
+// ---------------------------------------------------------------------------------------------
+template <typename T> struct Vec16;                       // one 16-byte load worth of elements
+template <> struct Vec16<double> { double v[2]; };
+template <> struct Vec16<float> { float v[4]; };
+template <typename T> constexpr int kVecElems = 16 / (int)sizeof(T);
+
+__device__ __forceinline__ Vec16<double> ldg_stream16(const double *ptr, uint64_t policy)
+{
+    const double2 t = ldg_stream_f64x2(ptr, policy);
+    Vec16<double> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    return r;
+}
+__device__ __forceinline__ Vec16<float> ldg_stream16(const float *ptr, uint64_t policy)
+{
+    Vec16<float> r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
+                 : "l"(ptr), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ Vec16<double> ldg_vec16(const double *ptr)
+{
+    const double2 t = __ldg(reinterpret_cast<const double2 *>(ptr));
+    Vec16<double> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    return r;
+}
+__device__ __forceinline__ Vec16<float> ldg_vec16(const float *ptr)
+{
+    const float4 t = __ldg(reinterpret_cast<const float4 *>(ptr));
+    Vec16<float> r;
+    r.v[0] = t.x;
+    r.v[1] = t.y;
+    r.v[2] = t.z;
+    r.v[3] = t.w;
+    return r;
+}
+// acc + a*b in fp64: unfused like the reference for doubles; for floats the product is exact in fp64
+__device__ __forceinline__ double prod_acc(double a, double b, double acc) { return __dadd_rn(__dmul_rn(a, b), acc); }
+__device__ __forceinline__ double prod_acc(float a, float b, double acc) { return __dadd_rn(__dmul_rn((double)a, (double)b), acc); }
+// s*x + y in the STORAGE precision, unfused (axpby of the reference with the scalar rounded to T first)
+__device__ __forceinline__ double scale_add(double s, double x, double y) { return __dadd_rn(__dmul_rn(s, x), y); }
+__device__ __forceinline__ float scale_add(double s, float x, float y) { return __fadd_rn(__fmul_rn((float)s, x), y); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {

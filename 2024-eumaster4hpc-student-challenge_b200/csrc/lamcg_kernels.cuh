@@ -18,9 +18,9 @@
 namespace lamcgk {
 
 struct GemvArgs {
-    const double *A;    // [rows][lda] row block of this rank, lda % 16 == 0, pad columns are zero
-    const double *p;    // [lda] full direction vector, zero padded
-    double *Ap;         // [rows]
+    const void *A;      // [rows][lda] row block of this rank (element type T of the handle), lda % 16 == 0, pad columns zero
+    const void *p;      // [lda] full direction vector, zero padded
+    void *Ap;           // [rows]
     double *partials;   // [grid] per-CTA partials of p.Ap
     DevState *st;
     long long rows;     // local rows
@@ -70,6 +70,8 @@ struct GemvTmaCfg {
 template <int RB, int CB, int STAGES>
 __global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_tma_kernel(GemvArgs g)
 {
+    const double *gA = static_cast<const double *>(g.A), *gp = static_cast<const double *>(g.p);
+    double *gAp = static_cast<double *>(g.Ap);
     using Cfg = GemvTmaCfg<RB, CB, STAGES>;
     constexpr int NW = Cfg::kConsumerWarps;
     static_assert(RB <= 32, "final reduction assumes RB <= 32");
@@ -123,9 +125,9 @@ __global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_
             double *tile = tiles + (size_t)s * Cfg::kStageDoubles;
             if (lane == 0) mbar_arrive_expect_tx(&full[s], seg * (uint32_t)(nr + 1));
             __syncwarp();
-            const double *src = g.A + prow * g.lda + c0;
+            const double *src = gA + prow * g.lda + c0;
             for (int r = lane; r < nr; r += 32) tma_load_1d(tile + r * CB, src + (long long)r * g.lda, seg, &full[s], polA);
-            if (lane == (RB & 31)) tma_load_1d(tile + RB * CB, g.p + c0, seg, &full[s], polP);
+            if (lane == (RB & 31)) tma_load_1d(tile + RB * CB, gp + c0, seg, &full[s], polP);
             if (++k == nchunk) { k = 0; ++pass; }
             if (++s == STAGES) { s = 0; ph ^= 1u; }
         }
@@ -179,8 +181,8 @@ __global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_
                 double sum = 0.0;
 #pragma unroll
                 for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, red[w * RB + lane]);
-                g.Ap[prow + lane] = sum;
-                contrib = __dmul_rn(g.p[g.row_offset + prow + lane], sum);
+                gAp[prow + lane] = sum;
+                contrib = __dmul_rn(gp[g.row_offset + prow + lane], sum);
             }
             contrib = warp_sum(contrib);
             cta_dot = __dadd_rn(cta_dot, contrib);
@@ -209,6 +211,8 @@ constexpr size_t kLdgSmemBytes = (size_t)kLdgPStages * kLdgPChunk * 8 + 2 * kLdg
 template <int R, int U, int PF = 0, int CPS = 2>
 __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs g)
 {
+    const double *gA = static_cast<const double *>(g.A), *gp = static_cast<const double *>(g.p);
+    double *gAp = static_cast<double *>(g.Ap);
     constexpr int NW = kLdgWarps, PCH = kLdgPChunk, PST = kLdgPStages;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     double *pbuf = reinterpret_cast<double *>(smem_raw);
@@ -252,7 +256,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs 
         const long long cl = g.lda - c0;
         const uint32_t bytes = (uint32_t)((cl < PCH ? cl : PCH) * 8);
         mbar_arrive_expect_tx(&full[ss], bytes);
-        tma_load_1d(pbuf + (size_t)ss * PCH, g.p + c0, bytes, &full[ss], polP);
+        tma_load_1d(pbuf + (size_t)ss * PCH, gp + c0, bytes, &full[ss], polP);
     };
     if (is_producer) {
         for (long long jj = 0; jj < PST - 1 && jj < total; ++jj) issue(jj);
@@ -266,7 +270,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs 
         const int nr = leftw <= 0 ? 0 : (leftw < R ? (int)leftw : R);
         const double *arow[R];
 #pragma unroll
-        for (int r = 0; r < R; ++r) arow[r] = g.A + (wrow + (r < nr ? r : 0)) * g.lda;
+        for (int r = 0; r < R; ++r) arow[r] = gA + (wrow + (r < nr ? r : 0)) * g.lda;
         double acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = 0.0;
@@ -314,8 +318,8 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs 
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 if (r < nr) {
-                    g.Ap[wrow + r] = acc[r];
-                    warp_dot = mul_add(g.p[g.row_offset + wrow + r], acc[r], warp_dot);
+                    gAp[wrow + r] = acc[r];
+                    warp_dot = mul_add(gp[g.row_offset + wrow + r], acc[r], warp_dot);
                 }
             }
         }
@@ -340,13 +344,16 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs 
 // sit in registers and are reused for the R rows (p is read from L2 once per R rows); R accumulators per
 // thread are reduced across the CTA at the end of the pass.  No shared-memory staging, no mbarriers.
 // =============================================================================================
-template <int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0>
+template <typename T, int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0>
 __global__ void __launch_bounds__(NT, CPS) gemv_ctarow_kernel(GemvArgs g)
 {
-    constexpr int CH = NT * U * 2; // columns per chunk (2048 for the default shape)
+    constexpr int E = kVecElems<T>;        // elements per 16-byte load: 2 doubles / 4 floats
+    constexpr int CH = NT * U * E;         // columns per chunk (4096 doubles for the default shape)
     constexpr int NWARP = NT / 32;
     static_assert(R <= 32, "row sums are finished by one warp");
     __shared__ double red[NWARP][R];
+    const T *gA = static_cast<const T *>(g.A), *gp = static_cast<const T *>(g.p);
+    T *gAp = static_cast<T *>(g.Ap);
     if (g.check_done && ld_volatile_int(&g.st->done)) return;
     const unsigned long long seq = gemv_peer_prologue(g);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -358,36 +365,49 @@ __global__ void __launch_bounds__(NT, CPS) gemv_ctarow_kernel(GemvArgs g)
     double cta_dot = 0.0;
     for (long long pr = 0; pr < rcnt; pr += R) {
         const int nr = rcnt - pr < R ? (int)(rcnt - pr) : R;
-        const double *arow0 = g.A + (r0 + pr) * g.lda;
+        const T *arow0 = gA + (r0 + pr) * g.lda;
         double acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = 0.0;
         for (long long c0 = 0; c0 < g.lda; c0 += CH) {
-            double2 pv[U];
+            Vec16<T> pv[U];
             bool cv[U];
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                const long long c = c0 + 2 * tid + (long long)u * NT * 2;
+                const long long c = c0 + E * tid + (long long)u * NT * E;
                 cv[u] = c < g.lda;
-                pv[u] = cv[u] ? __ldg(reinterpret_cast<const double2 *>(g.p + c)) : make_double2(0.0, 0.0);
+                if (cv[u]) pv[u] = ldg_vec16(gp + c);
+                else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) pv[u].v[e] = T(0);
+                }
             }
-            double2 a[R][U];
+            Vec16<T> a[R][U];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    const long long c = c0 + 2 * tid + (long long)u * NT * 2;
-                    a[r][u] = (cv[u] && r < nr) ? (PF ? ldg_stream_f64x2_pf256(arow0 + (long long)r * g.lda + c, polA)
-                                                      : ldg_stream_f64x2(arow0 + (long long)r * g.lda + c, polA))
-                                                : make_double2(0.0, 0.0);
+                    const long long c = c0 + E * tid + (long long)u * NT * E;
+                    if (cv[u] && r < nr) {
+                        if constexpr (PF && sizeof(T) == 8) {
+                            const double2 t2 = ldg_stream_f64x2_pf256(reinterpret_cast<const double *>(arow0 + (long long)r * g.lda + c), polA);
+                            a[r][u].v[0] = t2.x;
+                            a[r][u].v[1] = t2.y;
+                        } else {
+                            a[r][u] = ldg_stream16(arow0 + (long long)r * g.lda + c, polA);
+                        }
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < E; ++e) a[r][u].v[e] = T(0);
+                    }
                 }
             }
 #pragma unroll
             for (int r = 0; r < R; ++r) {
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
-                    acc[r] = mul_add(a[r][u].x, pv[u].x, acc[r]);
-                    acc[r] = mul_add(a[r][u].y, pv[u].y, acc[r]);
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[r] = prod_acc(a[r][u].v[e], pv[u].v[e], acc[r]);
                 }
             }
         }
@@ -404,8 +424,9 @@ __global__ void __launch_bounds__(NT, CPS) gemv_ctarow_kernel(GemvArgs g)
                 double sum = 0.0;
 #pragma unroll
                 for (int w = 0; w < NWARP; ++w) sum = __dadd_rn(sum, red[w][lane]);
-                g.Ap[r0 + pr + lane] = sum;
-                contrib = __dmul_rn(g.p[g.row_offset + r0 + pr + lane], sum);
+                const T stored = (T)sum;
+                gAp[r0 + pr + lane] = stored;
+                contrib = __dmul_rn((double)gp[g.row_offset + r0 + pr + lane], (double)stored);
             }
             contrib = warp_sum(contrib);
             cta_dot = __dadd_rn(cta_dot, contrib);
@@ -423,9 +444,9 @@ struct VecArgs {
     DevState *st;
     const double *pAp_src;  // &st->pAp_local (single rank) or &st->pAp (after the NCCL all-reduce)
     const double *rrn_src;  // &st->rrn_local or &st->rrn
-    double *x, *r, *Ap;     // local slices [rows]
-    const double *p_in;     // [lda] full p of this iteration
-    double *p_out;          // [lda] full p of the next iteration (== p_in except in peer mode)
+    void *x, *r, *Ap;       // local slices [rows], element type T of the handle
+    const void *p_in;       // [lda] full p of this iteration
+    void *p_out;            // [lda] full p of the next iteration (== p_in except in peer mode)
     double *partials;       // [grid]
     double *hist;           // [hist_cap] sqrt(rr/bb) per iteration (nullable)
     long long rows, row_offset;
@@ -433,11 +454,14 @@ struct VecArgs {
     PeerView pv;            // pv.nranks <= 1: no peer exchange
 };
 
+template <typename T>
 __global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
 {
     __shared__ double scratch[32];
     __shared__ double s_pAp;
     DevState *st = v.st;
+    T *vx = static_cast<T *>(v.x), *vr = static_cast<T *>(v.r);
+    const T *vAp = static_cast<const T *>(v.Ap);
     if (ld_volatile_int(&st->done)) return;
     unsigned long long seq = 0ull;
     double pAp;
@@ -453,14 +477,14 @@ __global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
     }
     const double alpha = st->rr[v.par] / pAp;
     const double nalpha = -alpha;
-    const double *p = v.p_in + v.row_offset;
+    const T *p = static_cast<const T *>(v.p_in) + v.row_offset;
     double local = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x) {
-        // axpby(alpha, p, 1.0, x) and axpby(-alpha, Ap, 1.0, r): alpha*x[i] + beta*y[i], unfused
-        v.x[i] = __dadd_rn(__dmul_rn(alpha, p[i]), v.x[i]);
-        const double rn = __dadd_rn(__dmul_rn(nalpha, v.Ap[i]), v.r[i]);
-        v.r[i] = rn;
-        local = mul_add(rn, rn, local);
+        // axpby(alpha, p, 1.0, x) and axpby(-alpha, Ap, 1.0, r): alpha*x[i] + beta*y[i], unfused, in T
+        vx[i] = scale_add(alpha, p[i], vx[i]);
+        const T rn = scale_add(nalpha, vAp[i], vr[i]);
+        vr[i] = rn;
+        local = prod_acc(rn, rn, local);
     }
     const double cta = block_sum(local, scratch);
     if (threadIdx.x < 32) {
@@ -478,11 +502,13 @@ __global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
 // The p update is skipped on the final iteration (converged — as in the reference, which breaks
 // before it — or max_iters reached, where nobody reads p again).
 // =============================================================================================
+template <typename T>
 __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
 {
     __shared__ double s_rrn;
     __shared__ int s_last;
     DevState *st = v.st;
+    const T *vr = static_cast<const T *>(v.r);
     if (ld_volatile_int(&st->done)) return;
     const int it0 = st->iter[v.par];
     double rr_new;
@@ -508,11 +534,11 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
     const bool fin = conv || broke || it >= st->max_iters;
 
     if (!fin) {
-        const double *p = v.p_in + v.row_offset;
+        const T *p = static_cast<const T *>(v.p_in) + v.row_offset;
         if (v.pv.nranks > 1) {
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x) {
-                const double pn = __dadd_rn(v.r[i], __dmul_rn(beta, p[i]));
-                for (int q = 0; q < v.pv.nranks; ++q) peer_p(v.pv, q, v.par ^ 1)[v.row_offset + i] = pn;
+                const T pn = scale_add(beta, p[i], vr[i]);
+                for (int q = 0; q < v.pv.nranks; ++q) peer_p<T>(v.pv, q, v.par ^ 1)[v.row_offset + i] = pn;
             }
             __threadfence_system();
             __syncthreads();
@@ -529,9 +555,9 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
                 }
             }
         } else {
-            double *po = v.p_out + v.row_offset;
+            T *po = static_cast<T *>(v.p_out) + v.row_offset;
             for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x)
-                po[i] = __dadd_rn(v.r[i], __dmul_rn(beta, p[i])); // axpby(1.0, r, beta, p)
+                po[i] = scale_add(beta, p[i], vr[i]); // axpby(1.0, r, beta, p)
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -553,13 +579,15 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
 // Solution gather in peer mode (lamcg_get_solution): every rank stores its x slice into buffer
 // `buf` of every rank's exchange area, then raises gather_flag; the wait kernel blocks the stream
 // until all slices have landed locally.
-__global__ void __launch_bounds__(256) peer_gather_put_kernel(PeerView pv, const double *x, long long rows, long long row_offset,
+template <typename T>
+__global__ void __launch_bounds__(256) peer_gather_put_kernel(PeerView pv, const void *x_, long long rows, long long row_offset,
                                                                int buf, unsigned long long gseq, DevState *st)
 {
     __shared__ int s_last;
+    const T *x = static_cast<const T *>(x_);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < rows; i += (long long)gridDim.x * blockDim.x) {
-        const double xi = x[i];
-        for (int q = 0; q < pv.nranks; ++q) peer_xg(pv, q, buf)[row_offset + i] = xi;
+        const T xi = x[i];
+        for (int q = 0; q < pv.nranks; ++q) peer_xg<T>(pv, q, buf)[row_offset + i] = xi;
     }
     __threadfence_system();
     __syncthreads();
@@ -589,27 +617,30 @@ __global__ void __launch_bounds__(32) peer_gather_wait_kernel(PeerView pv, unsig
 // =============================================================================================
 struct InitArgs {
     DevState *st;
-    const double *b_full; // [lda] zero padded
-    double *x, *r, *Ap, *p_full;
+    const void *b_full; // [lda] zero padded, element type T
+    void *x, *r, *Ap, *p_full;
     long long n, lda, rows, row_offset;
     double eps;
     unsigned long long seq_base;
     int max_iters, hist_cap;
 };
 
+template <typename T>
 __global__ void __launch_bounds__(1024) init_solve_kernel(InitArgs a)
 {
     __shared__ double scratch[32];
+    const T *b = static_cast<const T *>(a.b_full);
+    T *px = static_cast<T *>(a.x), *pr = static_cast<T *>(a.r), *pAp = static_cast<T *>(a.Ap), *pp = static_cast<T *>(a.p_full);
     double local = 0.0;
     for (long long i = threadIdx.x; i < a.lda; i += blockDim.x) {
-        const double bi = a.b_full[i];
-        a.p_full[i] = bi;
-        local = mul_add(bi, bi, local);
+        const T bi = b[i];
+        pp[i] = bi;
+        local = prod_acc(bi, bi, local);
     }
     for (long long i = threadIdx.x; i < a.rows; i += blockDim.x) {
-        a.x[i] = 0.0;
-        a.Ap[i] = 0.0;
-        a.r[i] = a.b_full[a.row_offset + i];
+        px[i] = T(0);
+        pAp[i] = T(0);
+        pr[i] = b[a.row_offset + i];
     }
     const double bb = block_sum(local, scratch);
     if (threadIdx.x == 0) {
@@ -640,26 +671,30 @@ __global__ void __launch_bounds__(1024) init_solve_kernel(InitArgs a)
 // A[i][j] = 2 if g == j, 1 if |g - j| == 1, else 0; pad columns [n, lda) are zero.
 // Written by the GPU straight into the padded HBM layout, two doubles per store.
 // =============================================================================================
-__global__ void __launch_bounds__(256) generate_matrix_kernel(double *A, long long rows, long long n, long long lda, long long offset)
+template <typename T>
+__global__ void __launch_bounds__(256) generate_matrix_kernel(void *A_, long long rows, long long n, long long lda, long long offset)
 {
+    T *A = static_cast<T *>(A_);
     const long long half = lda >> 1;
     const long long total = rows * half;
     for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
         const long long i = t / half;
         const long long j = (t - i * half) * 2;
         const long long gr = i + offset;
-        double2 v;
         const long long d0 = gr - j, d1 = gr - (j + 1);
-        v.x = (j < n) ? (d0 == 0 ? 2.0 : ((d0 == 1 || d0 == -1) ? 1.0 : 0.0)) : 0.0;
-        v.y = (j + 1 < n) ? (d1 == 0 ? 2.0 : ((d1 == 1 || d1 == -1) ? 1.0 : 0.0)) : 0.0;
-        *reinterpret_cast<double2 *>(A + i * lda + j) = v;
+        const T v0 = (j < n) ? (d0 == 0 ? T(2) : ((d0 == 1 || d0 == -1) ? T(1) : T(0))) : T(0);
+        const T v1 = (j + 1 < n) ? (d1 == 0 ? T(2) : ((d1 == 1 || d1 == -1) ? T(1) : T(0))) : T(0);
+        A[i * lda + j] = v0;
+        A[i * lda + j + 1] = v1;
     }
 }
 
-__global__ void __launch_bounds__(256) fill_kernel(double *v, long long n, long long n_padded, double value)
+template <typename T>
+__global__ void __launch_bounds__(256) fill_kernel(void *v_, long long n, long long n_padded, double value)
 {
+    T *v = static_cast<T *>(v_);
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_padded; i += (long long)gridDim.x * blockDim.x)
-        v[i] = i < n ? value : 0.0;
+        v[i] = i < n ? (T)value : T(0);
 }
 
 // Read-only streaming ceiling: sum of every element of the row block with 128-bit loads.  Each CTA

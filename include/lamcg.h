@@ -65,6 +65,7 @@ typedef struct {
     int has_matrix, has_rhs;
     int gemv_variant;   /* resolved GEMV kernel: 1 = ldg, 2 = tma ring */
     int gemv_grid, gemv_block, gemv_smem_bytes;
+    int dtype;          /* 0 fp64, 1 fp32 */
 } lamcg_info;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -72,6 +73,12 @@ typedef struct {
 int lamcg_create(lamcg_t **out, int device);
 /* Rank `rank` of `nranks` of a row-partitioned job (MPI_Comm_rank/size in the reference). */
 int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks);
+/* Same with the element type of everything STORED (A, b, x and the work vectors): dtype 0 = fp64 (what the
+ * reference's drivers instantiate, and the type of lamcg_create / lamcg_create_ranked), 1 = fp32 (the <float>
+ * instantiation of the reference classes, GPU/local/ConjugateGradient_MultiGPUS_CUDA.cu:539).  With fp32 storage
+ * all reductions, alpha, beta and the stop test stay in fp64; files and caller buffers hold floats.  Every `void *`
+ * data argument below points at elements of the handle's type. */
+int lamcg_create_typed(lamcg_t **out, int device, int rank, int nranks, int dtype);
 void lamcg_destroy(lamcg_t *h);
 /* Last error message of this handle (or of the failed create when h == NULL). */
 const char *lamcg_last_error(const lamcg_t *h);
@@ -113,8 +120,8 @@ int lamcg_load_rhs(lamcg_t *h, const char *path);
  * (test/test_CG_CPU_OMP.cpp:76-79).  A is row-major with leading dimension n and may be a host
  * or a device pointer.  layout 0: A is the whole n*n matrix (the rank takes its rows);
  * layout 1: A is only this rank's local_rows*n block. */
-int lamcg_set_matrix(lamcg_t *h, const double *A, size_t n, int layout);
-int lamcg_set_rhs(lamcg_t *h, const double *b, size_t n);
+int lamcg_set_matrix(lamcg_t *h, const void *A, size_t n, int layout);
+int lamcg_set_rhs(lamcg_t *h, const void *b, size_t n);
 
 /* Random SPD system like challenge/main/random_spd_system.cpp (there: Intel MKL on the host):
  * Q = recursive block Gram-Schmidt of a U(-1,1) matrix drawn with glibc srand(seed)/rand(),
@@ -130,9 +137,9 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out);
 /* sqrt(rr/bb) after each executed iteration of the last solve; returns the count copied. */
 int lamcg_get_residual_history(lamcg_t *h, double *out, int capacity);
 /* This rank's slice of x (local_rows doubles, host pointer). */
-int lamcg_get_solution_local(lamcg_t *h, double *x_local);
+int lamcg_get_solution_local(lamcg_t *h, void *x_local);
 /* The whole x (n doubles, host pointer); collective over all ranks when nranks > 1. */
-int lamcg_get_solution(lamcg_t *h, double *x);
+int lamcg_get_solution(lamcg_t *h, void *x);
 /* save_result_to_file (OMP.hpp:199-217): header (n, 1) + x; collective, rank 0 writes.  Unlike
  * the reference the cols word is a clean 1 (SURVEY §2.4 defect 1) and x, not b, is written
  * (defect 2). */
@@ -141,7 +148,7 @@ int lamcg_save_solution(lamcg_t *h, const char *path);
 /* ---- measurement / test hooks ---------------------------------------------------------------- */
 /* One GEMV of the solver's own kernel on this rank's block: y_local = A_local * p, and the fused
  * epilogue value sum_i p[row_offset+i]*y_local[i].  Host pointers; p has n entries. */
-int lamcg_gemv(lamcg_t *h, const double *p, double *y_local, double *p_dot_y);
+int lamcg_gemv(lamcg_t *h, const void *p, void *y_local, double *p_dot_y);
 /* Launch the GEMV kernel `reps` times back to back on the solver's stream and return the average
  * device milliseconds per launch (CUDA events on that stream), after `warmup` untimed launches. */
 int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch);

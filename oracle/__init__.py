@@ -170,6 +170,46 @@ def cg_solve_generated(n: int, max_iters: int, rel_error: float, history: bool =
     return Result(bool(rc), it.value, rel.value, x, hist)
 
 
+def cg_solve_f32(A, b, max_iters: int, rel_error: float) -> Result:
+    """fp32 restatement (every variable a float), A = None selects the generate-mode matrix."""
+    L = lib()
+    fp = ctypes.POINTER(ctypes.c_float)
+    L.oracle_cg_solve_f32.restype = ctypes.c_int
+    L.oracle_cg_solve_f32.argtypes = [fp, fp, fp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, ctypes.POINTER(ctypes.c_int),
+                                      ctypes.POINTER(ctypes.c_float)]
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    n = b.size
+    x = np.zeros(n, dtype=np.float32)
+    it, rel = ctypes.c_int(), ctypes.c_float()
+    Ap = None
+    if A is not None:
+        A = np.ascontiguousarray(A, dtype=np.float32)
+        Ap = A.ctypes.data_as(fp)
+    rc = L.oracle_cg_solve_f32(Ap, b.ctypes.data_as(fp), x.ctypes.data_as(fp), n, max_iters, rel_error, ctypes.byref(it), ctypes.byref(rel))
+    assert rc >= 0
+    return Result(bool(rc), it.value, float(rel.value), x)
+
+
+def ref_omp_solve_f32(A, b, max_iters: int, rel_error: float, threads: int | None = None) -> Result:
+    """The unmodified reference's ConjugateGradient_CPU_OMP<float>::solve on an in-memory system."""
+    R = ref()
+    if threads:
+        R.ref_set_threads(threads)
+    fp = ctypes.POINTER(ctypes.c_float)
+    R.ref_omp_solve_f32.restype = ctypes.c_int
+    R.ref_omp_solve_f32.argtypes = [fp, fp, ctypes.c_size_t, ctypes.c_int, ctypes.c_float, fp, ctypes.POINTER(ctypes.c_int),
+                                    ctypes.POINTER(ctypes.c_float)]
+    A = np.ascontiguousarray(A, dtype=np.float32)
+    b = np.ascontiguousarray(b, dtype=np.float32)
+    n = b.size
+    x = np.zeros(n, dtype=np.float32)
+    it, rel = ctypes.c_int(), ctypes.c_float()
+    rc = R.ref_omp_solve_f32(A.ctypes.data_as(fp), b.ctypes.data_as(fp), n, max_iters, rel_error, x.ctypes.data_as(fp),
+                             ctypes.byref(it), ctypes.byref(rel))
+    assert rc >= 0, "could not parse the reference's output"
+    return Result(bool(rc), it.value, float(rel.value), x)
+
+
 def rand_fill(count: int, seed: int) -> np.ndarray:
     out = np.empty(count)
     lib().oracle_rand_fill(_dp(out), count, seed)

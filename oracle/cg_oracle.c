@@ -203,6 +203,71 @@ void oracle_rand_fill(double *out, size_t count, int seed)
     for (size_t i = 0; i < count; i++) out[i] = ((2.0 * rand()) / RAND_MAX) - 1.0;
 }
 
+/* ---------------------------------------------------------------------------------------------
+ * fp32 restatement: the same loop with every variable a float, i.e. what the reference's <float>
+ * instantiations compute (template parameter FloatingType = float in OMP.hpp:49-91,219-263).
+ * --------------------------------------------------------------------------------------------- */
+static float dot_f32(const float *x, const float *y, size_t size)
+{
+    float result = 0.0f;
+    for (size_t i = 0; i < size; i++) result += x[i] * y[i];
+    return result;
+}
+
+static void axpby_f32(float alpha, const float *x, float beta, float *y, size_t size)
+{
+    for (size_t i = 0; i < size; i++) y[i] = alpha * x[i] + beta * y[i];
+}
+
+void oracle_gemv_f32(const float *A, const float *x, float *y, size_t rows, size_t cols)
+{
+#pragma omp parallel for schedule(static)
+    for (size_t r = 0; r < rows; r++) {
+        float y_val = 0.0f;
+        const float *a = A + r * cols;
+        for (size_t c = 0; c < cols; c++) y_val += 1.0f * a[c] * x[c];
+        y[r] = 0.0f * y[r] + y_val;
+    }
+}
+
+/* A == NULL selects the generate-mode matrix (tridiag(1,2,1)) in structured form, as in matvec_generated. */
+int oracle_cg_solve_f32(const float *A, const float *b, float *x, size_t n, int max_iters, float rel_error,
+                        int *iters_out, float *rel_out)
+{
+    float *r = (float *)malloc(n * sizeof(float)), *p = (float *)malloc(n * sizeof(float)), *Ap = (float *)malloc(n * sizeof(float));
+    if (!r || !p || !Ap) { free(r); free(p); free(Ap); return -1; }
+    for (size_t i = 0; i < n; i++) { Ap[i] = 0.0f; x[i] = 0.0f; r[i] = b[i]; p[i] = b[i]; }
+    float alpha, beta, rr_new;
+    float rhs_module = dot_f32(b, b, n);
+    float rr = rhs_module;
+    int num_iters;
+    for (num_iters = 1; num_iters <= max_iters; num_iters++) {
+        if (A) {
+            oracle_gemv_f32(A, p, Ap, n, n);
+        } else {
+            for (size_t q = 0; q < n; q++) {
+                float y_val = 0.0f;
+                if (q > 0) y_val += 1.0f * 1.0f * p[q - 1];
+                y_val += 1.0f * 2.0f * p[q];
+                if (q + 1 < n) y_val += 1.0f * 1.0f * p[q + 1];
+                Ap[q] = 0.0f * Ap[q] + y_val;
+            }
+        }
+        alpha = rr / dot_f32(p, Ap, n);
+        axpby_f32(alpha, p, 1.0f, x, n);
+        axpby_f32(-alpha, Ap, 1.0f, r, n);
+        rr_new = dot_f32(r, r, n);
+        beta = rr_new / rr;
+        rr = rr_new;
+        if (sqrtf(rr / rhs_module) < rel_error) break;
+        axpby_f32(1.0f, r, beta, p, n);
+    }
+    if (iters_out) *iters_out = num_iters;
+    if (rel_out) *rel_out = sqrtf(rr / rhs_module);
+    free(r); free(p); free(Ap);
+    return num_iters <= max_iters ? 1 : 0;
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

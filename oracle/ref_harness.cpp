@@ -138,4 +138,32 @@ int ref_omp_solve(const double *A, const double *b, size_t n, int max_iters, dou
     return ok ? 1 : 0;
 }
 
+/* The <float> instantiation of the same reference class (in-memory system), for the fp32 path. */
+int ref_omp_solve_f32(const float *A, const float *b, size_t n, int max_iters, float rel_err, float *x_out, int *iters_out,
+                      float *rel_out)
+{
+    LAM::ConjugateGradient_CPU_OMP<float> cg;
+    cg._num_rows = n;
+    cg._num_cols = n;
+    cg._matrix = const_cast<float *>(A);
+    cg._rhs = const_cast<float *>(b);
+    cg._x = x_out;
+    cg._r = new float[n];
+    cg._p = new float[n];
+    cg._Ap = new float[n];
+    StdoutCapture cap;
+    bool ok = cg.solve(max_iters, rel_err);
+    std::string out = cap.finish();
+    delete[] cg._r; delete[] cg._p; delete[] cg._Ap;
+    int iters = 0;
+    float rel = 0;
+    int got;
+    if (ok) got = sscanf(out.c_str(), "Converged in %d iterations, relative error is %f", &iters, &rel);
+    else got = sscanf(out.c_str(), "Did not converge in %d iterations, relative error is %f", &iters, &rel);
+    if (got != 2) return -1;
+    if (iters_out) *iters_out = iters;
+    if (rel_out) *rel_out = rel;
+    return ok ? 1 : 0;
+}
+
 } // extern "C"

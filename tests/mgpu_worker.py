@@ -29,9 +29,9 @@ def main():
     report = {"comm": comm, "world": world, "cases": []}
     ok = True
 
-    def case(name, n, make_system, max_iters, loop_mode, tol):
+    def case(name, n, make_system, max_iters, loop_mode, tol, dtype="f64"):
         nonlocal ok
-        s = lamcg_b200.Solver(local, rank, world)
+        s = lamcg_b200.Solver(local, rank, world, dtype)
         lamcg_b200.launch.bootstrap_comm(s, n=n, mode=comm, dist=dist)
         s.set_option("loop_mode", loop_mode)
         ref = make_system(s)
@@ -110,6 +110,7 @@ def main():
     case("gen_tiny", 7, gen(7, 50), 50, 2, 1e-12)                     # fewer rows than CTAs, odd split
     case("spd_file", 1024, spd(1024, 11), 1000, 2, 1e-9)  # stops may differ by an iteration: see tests/test_gpu_parity.py X_TOL_STOPPED
     case("gen_big", 40000, gen(40000, 100), 100, 2, 1e-12)
+    case("gen_f32", 4100, gen(4100, 120), 120, 2, 1e-4, dtype="f32")  # fp32 storage across ranks (p slices, x gather in floats)
 
     if rank == 0:
         report["ok"] = bool(ok)
