@@ -11,6 +11,8 @@ Contents
 --------
 * ``cg_oracle.c``      our C restatement of the reference loop (-> ``liboracle_cg.so``)
 * ``ref_harness.cpp``  C-ABI window on the unmodified reference classes (-> ``_ref/libref_harness.so``)
+* ``ref_gpu_harness.cu`` command-line window on the unmodified reference GPU classes (-> ``_ref/ref_gpu_{single,multi}.out``);
+  ``_ref/test_CG_single_GPU.out`` / ``test_CG_MultiGPUS_CUDA.out`` are the reference's own GPU drivers, unmodified
 * ``mpi_shim/mpi.h``   1-rank MPI stand-in so the reference compiles without MPI
 * ``fileformat.py``    numpy restatement of the binary matrix/rhs/solution format
 * ``random_spd.py``    numpy restatement of ``random_spd_system.cpp``'s SPD distribution
@@ -29,6 +31,9 @@ REF_DIR = os.path.join(HERE, "_ref")
 REF_HARNESS_SO = os.path.join(REF_DIR, "libref_harness.so")
 REF_TEST_OMP = os.path.join(REF_DIR, "test_CG_CPU_OMP.out")
 REF_TEST_MPI_OMP = os.path.join(REF_DIR, "test_CG_CPU_MPI_OMP.out")
+REF_TEST_SINGLE_GPU = os.path.join(REF_DIR, "test_CG_single_GPU.out")
+REF_TEST_MULTI_GPU = os.path.join(REF_DIR, "test_CG_MultiGPUS_CUDA.out")
+REF_GPU_HARNESS = {"single": os.path.join(REF_DIR, "ref_gpu_single.out"), "multi": os.path.join(REF_DIR, "ref_gpu_multi.out")}
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 
@@ -40,7 +45,7 @@ def build(ref: bool | None = None) -> None:
     if ref is None:
         ref = os.path.isdir("/root/reference/challenge/main")
     if ref:
-        subprocess.run(["make", "-s", "-C", HERE, "ref"], check=True)
+        subprocess.run(["make", "-s", "-C", HERE, "ref", "refgpu"], check=True)
 
 
 def _dp(a: np.ndarray):
@@ -272,3 +277,27 @@ def ref_omp_solve(A: np.ndarray, b: np.ndarray, max_iters: int, rel_error: float
                          ctypes.byref(secs))
     assert rc >= 0, "could not parse the reference's output"
     return Result(bool(rc), it.value, rel.value, x, None, secs.value)
+
+
+# ------------------------------------------------------------------ the reference's GPU classes on this GPU (_ref, refgpu)
+def ref_gpu_available(variant: str = "single") -> bool:
+    return os.path.exists(REF_GPU_HARNESS[variant])
+
+
+def ref_gpu_solve(variant: str, max_iters, rel_error: float, n: int | None = None, A_path: str | None = None,
+                  b_path: str | None = None, x_path: str | None = None, timeout: float = 600.0) -> list[dict]:
+    """Run the unmodified reference GPU class (``single`` = ConjugateGradient_GPU_CUDA, ``multi`` =
+    ConjugateGradient_MultiGPUS_CUDA) in its own process through ``ref_gpu_harness.cu``: generate mode when ``n`` is
+    given, file mode otherwise.  ``max_iters`` may be a list: one solve per entry on the same resident host system
+    (the reference's solve() uploads A every call, so loop time = difference between two entries).  Returns one dict
+    per solve (iters as the class prints them, rel, wall seconds of solve()); x of the last solve goes to ``x_path``."""
+    import json
+    ks = [max_iters] if isinstance(max_iters, int) else list(max_iters)
+    exe = REF_GPU_HARNESS[variant]
+    if n is not None:
+        cmd = [exe, "gen", str(n)]
+    else:
+        cmd = [exe, "file", A_path, b_path]
+    cmd += [repr(float(rel_error)), x_path or "-"] + [str(k) for k in ks]
+    out = subprocess.run(cmd, check=True, capture_output=True, text=True, timeout=timeout).stdout
+    return [json.loads(line) for line in out.splitlines() if line.startswith("{")]
