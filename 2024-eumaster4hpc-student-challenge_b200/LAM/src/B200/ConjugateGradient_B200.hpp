@@ -111,22 +111,21 @@ public:
     bool solve(int max_iters, FloatingType rel_error) override
     {
         if (!h_ || !check(lamcg_solve(h_, max_iters, rel_error, &last_))) return false;
-        double gemv_ms = 0.0;
-        if (report_ == Report::Csv) lamcg_time_gemv(h_, 1, 3, &gemv_ms);
-        if (rank_ == 0) {
-            if (report_ == Report::Csv) {
-                const int its = last_.iterations_run > 0 ? last_.iterations_run : 1;
-                std::cout << gemv_ms * 1e-3 << "," << last_.solve_seconds / its << "," << last_.iterations << ","
-                          << last_.rel_residual << ",";
-            } else if (report_ == Report::Text) {
-                if (last_.converged)
-                    std::printf("Converged in %d iterations, relative error is %e\n", last_.iterations, last_.rel_residual);
-                else
-                    std::printf("Did not converge in %d iterations, relative error is %e\n", max_iters, last_.rel_residual);
-            }
-        }
+        report_solve(max_iters);
         return last_.converged != 0;
     }
+
+    // ---- beyond the reference: continue a solve that ran out of iterations / checkpoint it -------
+    // resume(m, eps) after solve(k, eps) that did not converge is bit-identical to solve(k + m, eps); reports totals.
+    bool resume(int more_iters, FloatingType rel_error)
+    {
+        if (!h_ || !check(lamcg_solve_resume(h_, more_iters, rel_error, &last_))) return false;
+        report_solve(last_.iterations - 1);
+        return last_.converged != 0;
+    }
+    // One file per rank: <filename> on one rank, <filename>.rank<r>of<P> otherwise.
+    bool save_checkpoint_to_file(const char *filename) const { return h_ && check(lamcg_checkpoint_save(h_, rank_path(filename).c_str())); }
+    bool load_checkpoint_from_file(const char *filename) { return h_ && check(lamcg_checkpoint_load(h_, rank_path(filename).c_str())); }
 
     bool load_matrix_from_file(const char *filename) override
     {
@@ -166,6 +165,27 @@ public:
     }
 
 private:
+    // what the reference's solve() prints: CSV fields (MPI_OMP.hpp:122-127) or the human line (OMP.hpp:80-90)
+    void report_solve(int max_iters)
+    {
+        double gemv_ms = 0.0;
+        if (report_ == Report::Csv) lamcg_time_gemv(h_, 1, 3, &gemv_ms);
+        if (rank_ != 0) return;
+        if (report_ == Report::Csv) {
+            const int its = last_.iterations_run > 0 ? last_.iterations_run : 1;
+            std::cout << gemv_ms * 1e-3 << "," << last_.solve_seconds / its << "," << last_.iterations << "," << last_.rel_residual << ",";
+        } else if (report_ == Report::Text) {
+            if (last_.converged)
+                std::printf("Converged in %d iterations, relative error is %e\n", last_.iterations, last_.rel_residual);
+            else
+                std::printf("Did not converge in %d iterations, relative error is %e\n", max_iters, last_.rel_residual);
+        }
+    }
+    std::string rank_path(const char *filename) const
+    {
+        if (nranks_ == 1) return filename;
+        return std::string(filename) + ".rank" + std::to_string(rank_) + "of" + std::to_string(nranks_);
+    }
     bool check(int rc) const
     {
         if (rc == LAMCG_OK) return true;

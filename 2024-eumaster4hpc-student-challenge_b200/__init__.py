@@ -97,6 +97,9 @@ _SIGNATURES = {
     "lamcg_get_solution_local": (ctypes.c_int, [_vp, _vp]),
     "lamcg_get_solution": (ctypes.c_int, [_vp, _vp]),
     "lamcg_save_solution": (ctypes.c_int, [_vp, _cp]),
+    "lamcg_solve_resume": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_double, ctypes.POINTER(lamcg_result)]),
+    "lamcg_checkpoint_save": (ctypes.c_int, [_vp, ctypes.c_char_p]),
+    "lamcg_checkpoint_load": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "lamcg_gemv": (ctypes.c_int, [_vp, _vp, _vp, _dp]),
     "lamcg_time_gemv": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp]),
     "lamcg_get_loop_profile": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
@@ -245,6 +248,20 @@ class Solver:
         self._ck(self._L.lamcg_solve(self._h, int(max_iters), float(rel_error), ctypes.byref(out)))
         return out
 
+    def solve_resume(self, more_iters: int, rel_error: float) -> lamcg_result:
+        """Carry on the last solve (it must have stopped on max_iters) for up to ``more_iters`` iterations;
+        bit-identical to one uninterrupted solve.  Totals are reported."""
+        out = lamcg_result()
+        self._ck(self._L.lamcg_solve_resume(self._h, int(more_iters), float(rel_error), ctypes.byref(out)))
+        return out
+
+    def checkpoint_save(self, path: str) -> None:
+        """This rank's x, r, p slices + scalars + iteration count (one file per rank)."""
+        self._ck(self._L.lamcg_checkpoint_save(self._h, os.fsencode(path)))
+
+    def checkpoint_load(self, path: str) -> None:
+        self._ck(self._L.lamcg_checkpoint_load(self._h, os.fsencode(path)))
+
     def residual_history(self, capacity: int | None = None) -> np.ndarray:
         cap = capacity if capacity is not None else 1 << 22
         buf = np.zeros(cap)
@@ -348,6 +365,32 @@ class ConjugateGradient_B200:
             else:
                 print("Did not converge in %d iterations, relative error is %e" % (max_iters, res.rel_residual))
         return bool(res.converged)
+
+    def resume(self, more_iters: int, rel_error: float) -> bool:
+        """Continue a solve that did not converge within max_iters (no reference equivalent: it restarts from x = 0)."""
+        try:
+            res = self._s.solve_resume(more_iters, rel_error)
+        except LamcgError as e:
+            if self._s.rank == 0:
+                print(e.message, file=sys.stderr)
+            return False
+        self.last_result = res
+        if self.verbose and self._s.rank == 0:
+            if res.converged:
+                print("Converged in %d iterations, relative error is %e" % (res.iterations, res.rel_residual))
+            else:
+                print("Did not converge in %d iterations, relative error is %e" % (res.iterations - 1, res.rel_residual))
+        return bool(res.converged)
+
+    def _rank_path(self, filename: str) -> str:
+        return filename if self._s.nranks == 1 else "%s.rank%dof%d" % (filename, self._s.rank, self._s.nranks)
+
+    def save_checkpoint_to_file(self, filename: str) -> bool:
+        """One file per rank (``<filename>.rank<r>of<P>`` when P > 1)."""
+        return self._try(self._s.checkpoint_save, self._rank_path(filename))
+
+    def load_checkpoint_from_file(self, filename: str) -> bool:
+        return self._try(self._s.checkpoint_load, self._rank_path(filename))
 
     def solve_system(self, A, b, x, max_iters: int, rel_error: float) -> bool:
         """The original challenge signature solve(A, b, x, size, max_iters, rel_error)

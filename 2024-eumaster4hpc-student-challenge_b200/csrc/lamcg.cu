@@ -6,6 +6,7 @@
 #include <mutex>
 #include <thread>
 #include <cerrno>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -101,6 +102,10 @@ struct lamcg {
     std::vector<cudaEvent_t> gemv_events;
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_ring[2] = {nullptr, nullptr};
     int last_hist_count = 0;
+    // resume / checkpoint: true while the device still holds the state of a solve that stopped on max_iters
+    bool resumable = false;
+    int done_iters = 0;                    // iterations that solve has executed
+    unsigned long long cur_seq_base = 0;   // its peer sequence base
     std::string err;
 
     int fail(int code, const char *fmt, ...)
@@ -421,16 +426,19 @@ int build_graph(lamcg *h, int chunk)
     return LAMCG_OK;
 }
 
-int ensure_hist(lamcg *h, int max_iters)
+int ensure_hist(lamcg *h, int max_iters, int keep)
 {
     if (!h->opt_history) return LAMCG_OK;
     int want = std::max(max_iters, 1);
     if (want > (1 << 22)) want = 1 << 22;
     if (h->hist_cap >= want) return LAMCG_OK;
+    double *grown = nullptr;
+    CK(cudaMalloc(&grown, (size_t)want * sizeof(double)));
+    if (keep > 0 && h->hist) // a resumed solve keeps the history of the iterations already done
+        CK(cudaMemcpyAsync(grown, h->hist, (size_t)std::min(keep, h->hist_cap) * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
     cudaFree(h->hist);
-    h->hist = nullptr;
-    h->hist_cap = 0;
-    CK(cudaMalloc(&h->hist, (size_t)want * sizeof(double)));
+    h->hist = grown;
     h->hist_cap = want;
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; } // hist pointer is baked in
     return LAMCG_OK;
@@ -542,6 +550,110 @@ int pread_full(int fd, void *buf, size_t bytes, off_t off)
         bytes -= (size_t)got;
     }
     return 0;
+}
+
+} // namespace
+
+namespace {
+
+int resolve_loop_mode(lamcg *h)
+{
+    int loop_mode = (int)h->opt_loop_mode;
+    if (loop_mode == kLoopAuto) {
+        if (h->opt_time_gemv) loop_mode = kLoopStream;
+        else if (h->nranks == 1 && h->dtype == 0 && h->n <= kPersistAutoMaxN) loop_mode = kLoopPersistent;
+        else loop_mode = kLoopGraph;
+    }
+    if (h->opt_time_gemv) loop_mode = kLoopStream;
+    return loop_mode;
+}
+
+// Enqueue iterations first_iter .. max_total-1 (0-based) on the stream / as graph launches, watch the device's `done`
+// latch one chunk behind, and report.  The device state (x, r, p, scalars, counters) must already be in place:
+// init_solve_kernel for a fresh solve, resume_kernel for a continued one.  `launches` counts what the caller enqueued.
+int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_result *out, int launches)
+{
+    int chunk = (int)std::max<long long>(2, h->opt_chunk_iters);
+    chunk += chunk & 1; // the parity double-buffering needs an even number of iterations per chunk
+    int rc;
+    if (loop_mode == kLoopGraph) {
+        rc = build_graph(h, chunk);
+        if (rc != LAMCG_OK) return rc;
+    }
+    const bool time_gemv = h->opt_time_gemv != 0 && max_total > first_iter;
+    if (time_gemv) {
+        const size_t need = 2 * (size_t)std::min(max_total - first_iter, 1 << 16);
+        while (h->gemv_events.size() < need) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            h->gemv_events.push_back(e);
+        }
+    }
+    CK(cudaEventRecord(h->ev_start, h->stream));
+    int launched = first_iter, c = 0, timed_iters = 0;
+    bool stop = false;
+    while (launched < max_total && !stop) {
+        if (loop_mode == kLoopGraph && (launched & 1) == 0) {
+            CK(cudaGraphLaunch(h->graph_exec, h->stream)); // the captured chunk starts on parity 0
+            launched += chunk;
+            launches += 3 * chunk;
+        } else {
+            const int count = loop_mode == kLoopGraph ? 1 : chunk; // graph loop resumed on an odd iteration: one plain step first
+            for (int i = 0; i < count && launched < max_total; ++i, ++launched) {
+                cudaEvent_t e0 = nullptr, e1 = nullptr;
+                const size_t k = (size_t)(launched - first_iter);
+                if (time_gemv && 2 * k + 1 < h->gemv_events.size()) {
+                    e0 = h->gemv_events[2 * k];
+                    e1 = h->gemv_events[2 * k + 1];
+                    timed_iters = (int)k + 1;
+                }
+                rc = enqueue_iteration(h, launched & 1, e0, e1, &launches);
+                if (rc != LAMCG_OK) return rc;
+            }
+        }
+        CK(cudaMemcpyAsync(&h->h_st[c & 1], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaEventRecord(h->ev_ring[c & 1], h->stream));
+        if (c >= 1) { // one chunk of look-ahead: inspect the chunk before the one just enqueued
+            CK(cudaEventSynchronize(h->ev_ring[(c - 1) & 1]));
+            const DevState &s = h->h_st[(c - 1) & 1];
+            if (s.done || s.error) stop = true;
+        }
+        ++c;
+    }
+    CK(cudaEventRecord(h->ev_stop, h->stream));
+    CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "the CG loop faulted on the device: %s", cudaGetErrorString(se));
+    const DevState &s = h->h_st[2];
+    rc = check_device_error(h, s);
+    if (rc != LAMCG_OK) return rc;
+
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
+    double gemv_ms = 0.0;
+    if (time_gemv) {
+        const int cnt = std::min(timed_iters, s.iters_done - first_iter);
+        for (int i = 0; i < cnt; ++i) {
+            float t = 0.f;
+            CK(cudaEventElapsedTime(&t, h->gemv_events[2 * i], h->gemv_events[2 * i + 1]));
+            gemv_ms += t;
+        }
+    }
+    h->last_hist_count = h->opt_history ? std::min(s.iters_done, h->hist_cap) : 0;
+    // x, r, the p of the last iteration, beta and rr are still on the device: a solve that ran out of iterations can go on
+    h->resumable = !s.converged && !s.breakdown && s.iters_done >= 1 && s.iters_done == max_total;
+    h->done_iters = s.iters_done;
+    if (out) {
+        out->converged = s.converged;
+        out->iterations = s.converged ? s.iters_done : (max_total < 0 ? 1 : max_total + 1);
+        out->rel_residual = std::sqrt(s.rr_final / s.bb);
+        out->solve_seconds = ms * 1e-3;
+        out->gemv_seconds = gemv_ms * 1e-3;
+        out->iterations_run = s.iters_done;
+        out->kernel_launches = launches;
+        out->numerical_breakdown = s.breakdown;
+    }
+    return LAMCG_OK;
 }
 
 } // namespace
@@ -809,6 +921,7 @@ int lamcg_comm_init_peer(lamcg_t *h, const void *all_handles)
 int lamcg_generate_matrix(lamcg_t *h, size_t rows, size_t cols)
 {
     if (!h) return LAMCG_ERR_INVALID;
+    h->resumable = false; // the device state of the last solve no longer matches the system
     if (rows != cols) return h->fail(LAMCG_ERR_SHAPE, "Matrix has to be square");
     int rc = alloc_system(h, rows);
     if (rc != LAMCG_OK) return rc;
@@ -832,6 +945,7 @@ int lamcg_generate_matrix(lamcg_t *h, size_t rows, size_t cols)
 int lamcg_generate_rhs(lamcg_t *h)
 {
     if (!h) return LAMCG_ERR_INVALID;
+    h->resumable = false; // the device state of the last solve no longer matches the system
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "generate_rhs before a matrix exists");
     CK(cudaSetDevice(h->device));
     const int grid = (int)std::min<size_t>((h->lda + 255) / 256, (size_t)h->sm_count * 4);
@@ -846,6 +960,7 @@ int lamcg_generate_rhs(lamcg_t *h)
 int lamcg_set_matrix(lamcg_t *h, const void *A, size_t n, int layout)
 {
     if (!h || !A) return LAMCG_ERR_INVALID;
+    h->resumable = false; // the device state of the last solve no longer matches the system
     int rc = alloc_system(h, n);
     if (rc != LAMCG_OK) return rc;
     const char *src = layout == 0 ? static_cast<const char *>(A) + h->row_offset * n * h->esz : static_cast<const char *>(A);
@@ -861,6 +976,7 @@ int lamcg_set_matrix(lamcg_t *h, const void *A, size_t n, int layout)
 int lamcg_set_rhs(lamcg_t *h, const void *b, size_t n)
 {
     if (!h || !b) return LAMCG_ERR_INVALID;
+    h->resumable = false; // the device state of the last solve no longer matches the system
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "set_rhs before a matrix exists");
     if (n != h->n) return h->fail(LAMCG_ERR_SHAPE, "Size of right hand side does not match the matrix");
     CK(cudaSetDevice(h->device));
@@ -873,6 +989,7 @@ int lamcg_set_rhs(lamcg_t *h, const void *b, size_t n)
 int lamcg_load_matrix(lamcg_t *h, const char *path)
 {
     if (!h || !path) return LAMCG_ERR_INVALID;
+    h->resumable = false; // the device state of the last solve no longer matches the system
     int fd = open(path, O_RDONLY);
     if (fd < 0) return h->fail(LAMCG_ERR_IO, "Cannot open %s: %s", path, strerror(errno));
     size_t rows = 0, cols = 0;
@@ -956,6 +1073,7 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
 int lamcg_load_rhs(lamcg_t *h, const char *path)
 {
     if (!h || !path) return LAMCG_ERR_INVALID;
+    h->resumable = false; // the device state of the last solve no longer matches the system
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "load_rhs before a matrix exists");
     int fd = open(path, O_RDONLY);
     if (fd < 0) return h->fail(LAMCG_ERR_IO, "Cannot open %s: %s", path, strerror(errno));
@@ -980,32 +1098,12 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     if (!h->has_matrix || !h->has_rhs) return h->fail(LAMCG_ERR_STATE, "solve needs a matrix and a right hand side");
     if (h->nranks > 1 && h->comm_mode == kCommNone) return h->fail(LAMCG_ERR_STATE, "multi-rank solve before lamcg_comm_init_*");
     CK(cudaSetDevice(h->device));
-    int rc = ensure_hist(h, max_iters);
+    h->resumable = false;
+    int rc = ensure_hist(h, max_iters, 0);
     if (rc != LAMCG_OK) return rc;
 
-    int loop_mode = (int)h->opt_loop_mode;
-    if (loop_mode == kLoopAuto) {
-        if (h->opt_time_gemv) loop_mode = kLoopStream;
-        else if (h->nranks == 1 && h->dtype == 0 && h->n <= kPersistAutoMaxN) loop_mode = kLoopPersistent;
-        else loop_mode = kLoopGraph;
-    }
-    if (h->opt_time_gemv) loop_mode = kLoopStream;
+    const int loop_mode = resolve_loop_mode(h);
     if (loop_mode == kLoopPersistent) return solve_persistent(h, max_iters, rel_error, out);
-    int chunk = (int)std::max<long long>(2, h->opt_chunk_iters);
-    chunk += chunk & 1; // the parity double-buffering needs an even number of iterations per chunk
-    if (loop_mode == kLoopGraph) {
-        rc = build_graph(h, chunk);
-        if (rc != LAMCG_OK) return rc;
-    }
-    const bool time_gemv = h->opt_time_gemv != 0 && max_iters > 0;
-    if (time_gemv) {
-        const size_t need = 2 * (size_t)std::min(max_iters, 1 << 16);
-        while (h->gemv_events.size() < need) {
-            cudaEvent_t e;
-            CK(cudaEventCreate(&e));
-            h->gemv_events.push_back(e);
-        }
-    }
 
     InitArgs ia;
     ia.st = h->st;
@@ -1014,7 +1112,7 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     ia.r = h->r;
     ia.Ap = h->Ap;
     ia.p_full = p_ptr(h, 0);
-    ia.seq_base = h->seq_next;
+    ia.seq_base = h->cur_seq_base = h->seq_next;
     h->seq_next += (unsigned long long)std::max(max_iters, 0) + 2ull;
     ia.n = (long long)h->n;
     ia.lda = (long long)h->lda;
@@ -1026,67 +1124,154 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     if (h->dtype == 0) init_solve_kernel<double><<<1, 1024, 0, h->stream>>>(ia);
     else init_solve_kernel<float><<<1, 1024, 0, h->stream>>>(ia);
     CK(cudaGetLastError());
-    int launches = 1;
+    return run_loop(h, loop_mode, 0, max_iters, out, 1);
+}
 
-    CK(cudaEventRecord(h->ev_start, h->stream));
-    int launched = 0, c = 0, timed_iters = 0;
-    bool stop = false;
-    while (launched < max_iters && !stop) {
-        if (loop_mode == kLoopGraph) {
-            CK(cudaGraphLaunch(h->graph_exec, h->stream));
-            launched += chunk;
-            launches += 3 * chunk;
-        } else {
-            for (int i = 0; i < chunk && launched < max_iters; ++i, ++launched) {
-                cudaEvent_t e0 = nullptr, e1 = nullptr;
-                if (time_gemv && 2 * (size_t)launched + 1 < h->gemv_events.size()) {
-                    e0 = h->gemv_events[2 * launched];
-                    e1 = h->gemv_events[2 * launched + 1];
-                    timed_iters = launched + 1;
-                }
-                rc = enqueue_iteration(h, launched & 1, e0, e1, &launches);
-                if (rc != LAMCG_OK) return rc;
-            }
-        }
-        CK(cudaMemcpyAsync(&h->h_st[c & 1], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
-        CK(cudaEventRecord(h->ev_ring[c & 1], h->stream));
-        if (c >= 1) { // one chunk of look-ahead: inspect the chunk before the one just enqueued
-            CK(cudaEventSynchronize(h->ev_ring[(c - 1) & 1]));
-            const DevState &s = h->h_st[(c - 1) & 1];
-            if (s.done || s.error) stop = true;
-        }
-        ++c;
-    }
-    CK(cudaEventRecord(h->ev_stop, h->stream));
-    CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
-    cudaError_t se = cudaStreamSynchronize(h->stream);
-    if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "the CG loop faulted on the device: %s", cudaGetErrorString(se));
-    const DevState &s = h->h_st[2];
-    rc = check_device_error(h, s);
+int lamcg_solve_resume(lamcg_t *h, int more_iters, double rel_error, lamcg_result *out)
+{
+    if (!h) return LAMCG_ERR_INVALID;
+    if (more_iters < 1) return h->fail(LAMCG_ERR_INVALID, "lamcg_solve_resume: more_iters must be >= 1");
+    if (!h->resumable)
+        return h->fail(LAMCG_ERR_STATE, "nothing to resume: the last solve converged, broke down, ran in the persistent loop "
+                                        "(set loop_mode 2) or the system changed since; or no checkpoint was loaded");
+    if (h->done_iters > INT_MAX - more_iters) return h->fail(LAMCG_ERR_INVALID, "iteration count overflows int");
+    CK(cudaSetDevice(h->device));
+    const int k = h->done_iters, total = k + more_iters;
+    int rc = ensure_hist(h, total, std::min(k, h->hist_cap));
     if (rc != LAMCG_OK) return rc;
+    int loop_mode = resolve_loop_mode(h);
+    if (loop_mode == kLoopPersistent) loop_mode = kLoopGraph; // the one-kernel loop always starts from x = 0
+    h->seq_next = std::max(h->seq_next, h->cur_seq_base + (unsigned long long)total + 2ull);
+    h->resumable = false;
+    // the deferred p update of iteration k (0-based k-1), then carry on with iteration index k
+    VecArgs v = vec_args(h, (k - 1) & 1);
+    const int vg = vec_grid(h);
+    const int hist_cap = h->opt_history ? h->hist_cap : 0;
+    if (h->dtype == 0) resume_kernel<double><<<vg, kVecThreads, 0, h->stream>>>(v, total, rel_error, hist_cap);
+    else resume_kernel<float><<<vg, kVecThreads, 0, h->stream>>>(v, total, rel_error, hist_cap);
+    CK(cudaGetLastError());
+    if (h->comm_mode == kCommNccl) {
+        rc = allgather_vec(h, h->p_full);
+        if (rc != LAMCG_OK) return rc;
+    }
+    return run_loop(h, loop_mode, k, total, out, 1);
+}
 
-    float ms = 0.f;
-    CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
-    double gemv_ms = 0.0;
-    if (time_gemv) {
-        const int cnt = std::min(timed_iters, s.iters_done);
-        for (int i = 0; i < cnt; ++i) {
-            float t = 0.f;
-            CK(cudaEventElapsedTime(&t, h->gemv_events[2 * i], h->gemv_events[2 * i + 1]));
-            gemv_ms += t;
+// ---- checkpoint / restart of a long solve ------------------------------------
+// One file per rank: a fixed header, then this rank's slices of x, r and of the p of the last executed
+// iteration, then the residual history kept so far.  Everything else the loop needs (A, b) is the system itself.
+namespace {
+struct CkptHeader {
+    char magic[8];            // "LAMCGCK1"
+    uint64_t n, local_rows, row_offset;
+    int32_t dtype, rank, nranks, iters_done;
+    double bb, rr, alpha_last, beta_last, eps;
+    int32_t hist_count, reserved;
+};
+const char kCkptMagic[8] = {'L', 'A', 'M', 'C', 'G', 'C', 'K', '1'};
+
+int write_full(int fd, const void *buf, size_t bytes)
+{
+    const char *c = static_cast<const char *>(buf);
+    while (bytes > 0) {
+        ssize_t put = write(fd, c, bytes);
+        if (put < 0) {
+            if (errno == EINTR) continue;
+            return -1;
         }
+        c += put;
+        bytes -= (size_t)put;
     }
-    h->last_hist_count = h->opt_history ? std::min(s.iters_done, h->hist_cap) : 0;
-    if (out) {
-        out->converged = s.converged;
-        out->iterations = s.converged ? s.iters_done : (max_iters < 0 ? 1 : max_iters + 1);
-        out->rel_residual = std::sqrt(s.rr_final / s.bb);
-        out->solve_seconds = ms * 1e-3;
-        out->gemv_seconds = gemv_ms * 1e-3;
-        out->iterations_run = s.iters_done;
-        out->kernel_launches = launches;
-        out->numerical_breakdown = s.breakdown;
+    return 0;
+}
+} // namespace
+
+int lamcg_checkpoint_save(lamcg_t *h, const char *path)
+{
+    if (!h || !path) return LAMCG_ERR_INVALID;
+    if (!h->resumable) return h->fail(LAMCG_ERR_STATE, "no resumable state to checkpoint (the last solve must have stopped on max_iters in the stream or graph loop)");
+    CK(cudaSetDevice(h->device));
+    const int k = h->done_iters;
+    CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
+    const size_t slice = h->local_rows * h->esz;
+    const int hist_count = h->opt_history ? std::min(k, h->hist_cap) : 0;
+    std::vector<char> buf(3 * slice + (size_t)hist_count * sizeof(double));
+    if (slice) {
+        CK(cudaMemcpyAsync(buf.data(), h->x, slice, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(buf.data() + slice, h->r, slice, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(buf.data() + 2 * slice, p_ptr(h, (k - 1) & 1) + h->row_offset * h->esz, slice, cudaMemcpyDeviceToHost, h->stream));
     }
+    if (hist_count) CK(cudaMemcpyAsync(buf.data() + 3 * slice, h->hist, (size_t)hist_count * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    const DevState &s = h->h_st[2];
+    CkptHeader hd{};
+    memcpy(hd.magic, kCkptMagic, 8);
+    hd.n = h->n; hd.local_rows = h->local_rows; hd.row_offset = h->row_offset;
+    hd.dtype = h->dtype; hd.rank = h->rank; hd.nranks = h->nranks; hd.iters_done = k;
+    hd.bb = s.bb; hd.rr = s.rr_final; hd.alpha_last = s.alpha_last; hd.beta_last = s.beta_last; hd.eps = s.eps;
+    hd.hist_count = hist_count;
+    int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    if (fd < 0) return h->fail(LAMCG_ERR_IO, "%s: cannot open for writing: %s", path, strerror(errno));
+    const bool ok = write_full(fd, &hd, sizeof hd) == 0 && write_full(fd, buf.data(), buf.size()) == 0;
+    const bool closed = close(fd) == 0;
+    if (!ok || !closed) return h->fail(LAMCG_ERR_IO, "%s: short write", path);
+    return LAMCG_OK;
+}
+
+int lamcg_checkpoint_load(lamcg_t *h, const char *path)
+{
+    if (!h || !path) return LAMCG_ERR_INVALID;
+    if (!h->has_matrix || !h->has_rhs) return h->fail(LAMCG_ERR_STATE, "load the system (matrix and rhs) before its checkpoint");
+    if (h->nranks > 1 && h->comm_mode == kCommNone) return h->fail(LAMCG_ERR_STATE, "multi-rank checkpoint load before lamcg_comm_init_*");
+    h->resumable = false;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return h->fail(LAMCG_ERR_IO, "%s: cannot open: %s", path, strerror(errno));
+    CkptHeader hd;
+    if (pread_full(fd, &hd, sizeof hd, 0) != 0 || memcmp(hd.magic, kCkptMagic, 8) != 0) {
+        close(fd);
+        return h->fail(LAMCG_ERR_IO, "%s: not a lamcg checkpoint", path);
+    }
+    if (hd.n != h->n || hd.local_rows != h->local_rows || hd.row_offset != h->row_offset || hd.dtype != h->dtype || hd.rank != h->rank ||
+        hd.nranks != h->nranks || hd.iters_done < 1 || hd.hist_count < 0 || hd.hist_count > hd.iters_done) {
+        close(fd);
+        return h->fail(LAMCG_ERR_SHAPE, "%s: checkpoint of rank %d/%d, n = %llu, dtype %d does not match this handle (rank %d/%d, n = %zu, dtype %d)", path,
+                       hd.rank, hd.nranks, (unsigned long long)hd.n, hd.dtype, h->rank, h->nranks, h->n, h->dtype);
+    }
+    const size_t slice = h->local_rows * h->esz;
+    std::vector<char> buf(3 * slice + (size_t)hd.hist_count * sizeof(double));
+    const int rd = buf.empty() ? 0 : pread_full(fd, buf.data(), buf.size(), (off_t)sizeof hd);
+    close(fd);
+    if (rd != 0) return h->fail(LAMCG_ERR_IO, "%s: truncated checkpoint", path);
+    CK(cudaSetDevice(h->device));
+    const int k = hd.iters_done;
+    int rc = ensure_hist(h, k, 0);
+    if (rc != LAMCG_OK) return rc;
+    if (slice) {
+        CK(cudaMemcpyAsync(h->x, buf.data(), slice, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(h->r, buf.data() + slice, slice, cudaMemcpyHostToDevice, h->stream));
+        CK(cudaMemcpyAsync(p_ptr(h, (k - 1) & 1) + h->row_offset * h->esz, buf.data() + 2 * slice, slice, cudaMemcpyHostToDevice, h->stream));
+    }
+    const int hist_keep = h->opt_history ? std::min(hd.hist_count, h->hist_cap) : 0;
+    if (hist_keep) CK(cudaMemcpyAsync(h->hist, buf.data() + 3 * slice, (size_t)hist_keep * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    // the scalar state exactly as K3 of iteration k left it (both parity slots hold the latest values)
+    DevState s{};
+    s.bb = hd.bb;
+    s.rr[0] = s.rr[1] = s.rr_final = hd.rr;
+    s.alpha_last = hd.alpha_last;
+    s.beta_last = hd.beta_last;
+    s.eps = hd.eps;
+    s.iter[0] = s.iter[1] = s.iters_done = k;
+    s.max_iters = k;
+    s.done = 1;
+    s.hist_cap = h->opt_history ? h->hist_cap : 0;
+    s.seq_base = h->cur_seq_base = h->seq_next;
+    h->seq_next += (unsigned long long)k + 2ull;
+    h->h_st[2] = s;
+    CK(cudaMemcpyAsync(h->st, &h->h_st[2], sizeof(DevState), cudaMemcpyHostToDevice, h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    h->last_hist_count = hist_keep;
+    h->done_iters = k;
+    h->resumable = true;
     return LAMCG_OK;
 }
 
@@ -1229,6 +1414,7 @@ void host_random_fill(double *out, size_t count, int seed)
 int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
 {
     if (!h || n == 0) return LAMCG_ERR_INVALID;
+    h->resumable = false; // the device state of the last solve no longer matches the system
     if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "the SPD generator runs on one rank (generate, save, then load row blocks)");
     if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "the SPD generator is fp64 only");
     int rc = alloc_system(h, n);
@@ -1316,6 +1502,7 @@ int lamcg_save_system(lamcg_t *h, const char *matrix_path, const char *rhs_path)
 int lamcg_gemv(lamcg_t *h, const void *p, void *y_local, double *p_dot_y)
 {
     if (!h || !p || !y_local) return LAMCG_ERR_INVALID;
+    h->resumable = false; // the device state of the last solve no longer matches the system
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
     CK(cudaSetDevice(h->device));
     CK(cudaMemsetAsync(p_ptr(h, 0), 0, h->lda * h->esz, h->stream));

@@ -507,6 +507,41 @@ __global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
     }
 }
 
+// p = r + beta p on this rank's rows: the second half of K3, also run on its own by resume_kernel.
+// Peer mode: the new slice goes straight into buffer [par^1] of every rank and the last CTA raises
+// p_flag[me] = seq_base + it on every rank once all stores are fenced (this IS the all-gather).
+template <typename T>
+__device__ __forceinline__ void p_update(const VecArgs &v, double beta, int it, int *s_last)
+{
+    DevState *st = v.st;
+    const T *vr = static_cast<const T *>(v.r);
+    const T *p = static_cast<const T *>(v.p_in) + v.row_offset;
+    if (v.pv.nranks > 1) {
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x) {
+            const T pn = scale_add(beta, p[i], vr[i]);
+            for (int q = 0; q < v.pv.nranks; ++q) peer_p<T>(v.pv, q, v.par ^ 1)[v.row_offset + i] = pn;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();
+            *s_last = (atomicAdd(&st->ticket_misc, 1u) == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (*s_last) {
+            if (threadIdx.x == 0) st->ticket_misc = 0u;
+            if ((int)threadIdx.x < v.pv.nranks) {
+                __threadfence_system();
+                st_release_sys_u64(&peer_hdr(v.pv, threadIdx.x)->p_flag[v.pv.me], st->seq_base + (unsigned long long)it);
+            }
+        }
+    } else {
+        T *po = static_cast<T *>(v.p_out) + v.row_offset;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x)
+            po[i] = scale_add(beta, p[i], vr[i]); // axpby(1.0, r, beta, p)
+    }
+}
+
 // =============================================================================================
 // K3: beta = rr_new / rr ; rr = rr_new ; stop test ; p = r + beta p   (OMP.hpp:75-78)
 // Every thread evaluates the (identical) scalars; thread 0 of CTA 0 commits them to the other
@@ -522,7 +557,6 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
     __shared__ double s_rrn;
     __shared__ int s_last;
     DevState *st = v.st;
-    const T *vr = static_cast<const T *>(v.r);
     if (ld_volatile_int(&st->done)) return;
     const int it0 = st->iter[v.par];
     double rr_new;
@@ -547,33 +581,7 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
     const bool broke = !(rel == rel) || isinf(rel) || !(beta == beta);
     const bool fin = conv || broke || it >= st->max_iters;
 
-    if (!fin) {
-        const T *p = static_cast<const T *>(v.p_in) + v.row_offset;
-        if (v.pv.nranks > 1) {
-            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x) {
-                const T pn = scale_add(beta, p[i], vr[i]);
-                for (int q = 0; q < v.pv.nranks; ++q) peer_p<T>(v.pv, q, v.par ^ 1)[v.row_offset + i] = pn;
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                __threadfence();
-                s_last = (atomicAdd(&st->ticket_misc, 1u) == gridDim.x - 1);
-            }
-            __syncthreads();
-            if (s_last) {
-                if (threadIdx.x == 0) st->ticket_misc = 0u;
-                if ((int)threadIdx.x < v.pv.nranks) {
-                    __threadfence_system();
-                    st_release_sys_u64(&peer_hdr(v.pv, threadIdx.x)->p_flag[v.pv.me], st->seq_base + (unsigned long long)it);
-                }
-            }
-        } else {
-            T *po = static_cast<T *>(v.p_out) + v.row_offset;
-            for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < v.rows; i += (long long)gridDim.x * blockDim.x)
-                po[i] = scale_add(beta, p[i], vr[i]); // axpby(1.0, r, beta, p)
-        }
-    }
+    if (!fin) p_update<T>(v, beta, it, &s_last);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->rr[v.par ^ 1] = rr_new;
         st->iter[v.par ^ 1] = it;
@@ -587,6 +595,24 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
             __threadfence();
             st->done = 1;
         }
+    }
+}
+
+// Continue a solve that stopped on max_iters (lamcg_solve_resume): K3 skipped the p update of its last
+// iteration, so do it now with the stored beta (v is built for the parity of that last iteration), then
+// raise the iteration cap and drop the `done` latch.  Iteration numbering, the scalar parity slots and the
+// peer sequence numbers simply carry on, which makes solve(k) + resume(m) bit-identical to solve(k + m).
+template <typename T>
+__global__ void __launch_bounds__(256) resume_kernel(VecArgs v, int new_max_iters, double eps, int hist_cap)
+{
+    __shared__ int s_last;
+    DevState *st = v.st;
+    p_update<T>(v, st->beta_last, st->iters_done, &s_last);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        st->max_iters = new_max_iters;
+        st->eps = eps;
+        st->hist_cap = hist_cap;
+        st->done = 0;
     }
 }
 

@@ -2,6 +2,9 @@
 // (challenge/main/test/test_CG_CPU_MPI_OMP.cpp / test_CG_MultiGPUS_CUDA_{MPI,NCCL}.cpp):
 //   -A <matrix> -b <rhs>   file mode          -s <n>   generate mode (exclusive with -A/-b)
 //   -o <sol> -i <max_iters> -e <rel_error> -v -h      defaults io/*.bin, 10000, 1e-9
+// Beyond the reference (its long generate-mode runs restart from x = 0):
+//   -c <file>   write a checkpoint (x, r, p, scalars; one file per rank) if the solve stops on max_iters
+//   -r <file>   restore that checkpoint after loading/generating the same system and run -i FURTHER iterations
 // Ranks: one process per GPU, LAMCG_NGPUS=<P> in the environment plays the role of `srun -n P`.
 // stdout (rank 0, not verbose) is the reference's one CSV line:
 //   n,ranks,threads,io_or_gen_s,avg_gemv_s,avg_iter_s,iters,rel_err,total_s
@@ -27,6 +30,7 @@ struct Args {
     double rel_error = 1e-9;
     size_t n = 0;
     bool generate = false, load = false, verbose = false;
+    const char *ckpt_out = nullptr, *ckpt_in = nullptr;
 };
 
 void usage(const char *prog)
@@ -39,6 +43,8 @@ void usage(const char *prog)
     std::printf("  -i <int>        Maximum number of iterations\n");
     std::printf("  -e <float>      Relative error\n");
     std::printf("  -s <int>        Generate matrix of size n x n\n");
+    std::printf("  -c <file>       Write a checkpoint if the solve stops on the iteration limit\n");
+    std::printf("  -r <file>       Resume from a checkpoint (-i counts further iterations)\n");
     std::printf("  -v              Verbose mode\n");
     std::printf("  -h              Show this help message\n");
 }
@@ -54,6 +60,7 @@ int run(LAM::RankWorld &world, const Args &a)
 
     LAM::ConjugateGradient_B200<double> cg(world.rank(), world.rank(), world.size(), LAM::Report::Csv);
     if (!cg.ok()) return 1;
+    if (a.ckpt_out) cg.set_option("loop_mode", 2); // the one-kernel loop for small n keeps p in shared memory: nothing to checkpoint
     size_t n_hint = a.n;
     if (!a.generate) { // file mode: the system size is the first header word (size_t rows)
         if (FILE *f = std::fopen(a.matrix, "rb")) {
@@ -89,8 +96,20 @@ int run(LAM::RankWorld &world, const Args &a)
 
     say("Solving the system ...\n");
     t0 = Clock::now();
-    cg.solve(a.max_iters, a.rel_error);
+    if (a.ckpt_in) {
+        if (!cg.load_checkpoint_from_file(a.ckpt_in)) {
+            if (root) std::fprintf(stderr, "Failed to read checkpoint\n");
+            return 3;
+        }
+        cg.resume(a.max_iters, a.rel_error);
+    } else {
+        cg.solve(a.max_iters, a.rel_error);
+    }
     const long long cg_ms = ms_since(t0);
+    if (a.ckpt_out && !cg.last_result().converged && !cg.last_result().numerical_breakdown && !cg.save_checkpoint_to_file(a.ckpt_out)) {
+        if (root) std::fprintf(stderr, "Failed to save checkpoint\n");
+        return 7;
+    }
     if (csv) {
         if (a.generate) std::cout << cg_ms / 1000; // whole seconds, as the reference prints in generate mode
         else std::cout << cg_ms / 1000.0;
@@ -119,7 +138,7 @@ int main(int argc, char **argv)
 {
     Args a;
     int opt;
-    while ((opt = getopt(argc, argv, "hvA:b:o:i:e:s:")) != -1) {
+    while ((opt = getopt(argc, argv, "hvA:b:o:i:e:s:c:r:")) != -1) {
         switch (opt) {
         case 'A':
         case 'b':
@@ -141,10 +160,12 @@ int main(int argc, char **argv)
         case 'o': a.sol = optarg; break;
         case 'i': a.max_iters = std::atoi(optarg); break;
         case 'e': a.rel_error = std::atof(optarg); break;
+        case 'c': a.ckpt_out = optarg; break;
+        case 'r': a.ckpt_in = optarg; break;
         case 'v': a.verbose = true; break;
         case 'h': usage(argv[0]); return 0;
         case '?':
-            if (optopt == 'A' || optopt == 'b' || optopt == 'o' || optopt == 'i' || optopt == 'e' || optopt == 's')
+            if (optopt == 'A' || optopt == 'b' || optopt == 'o' || optopt == 'i' || optopt == 'e' || optopt == 's' || optopt == 'c' || optopt == 'r')
                 std::fprintf(stderr, "Option -%c requires an argument.\n", optopt);
             else if (std::isprint(optopt))
                 std::fprintf(stderr, "Unknown option `-%c'.\n", optopt);

@@ -134,6 +134,20 @@ int lamcg_save_system(lamcg_t *h, const char *matrix_path, const char *rhs_path)
 /* ---- solve ---------------------------------------------------------------------------------- */
 /* solve(max_iters, rel_error) (OMP.hpp:49-91): x0 = 0, r = p = b; may be called repeatedly. */
 int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out);
+/* Continue the last solve for up to `more_iters` further iterations, exactly as if it had been called with
+ * max_iters + more_iters in the first place: x, r, p, rr and the iteration counter are still on the device, so
+ * solve(k) followed by resume(m) is bit-identical to solve(k + m).  Needs a solve (stream or graph loop; set
+ * loop_mode 2 for n <= 4096) that stopped on max_iters without converging, or a loaded checkpoint, and an unchanged
+ * system; otherwise LAMCG_ERR_STATE.  `out` reports totals (iterations, iterations_run count from the original
+ * start; solve_seconds is this call's loop time).  Collective over all ranks.  The reference has no equivalent: its
+ * long generate-mode runs (n/2 iterations to converge, MPI_OMP.hpp:71-142) restart from x = 0. */
+int lamcg_solve_resume(lamcg_t *h, int more_iters, double rel_error, lamcg_result *out);
+/* Checkpoint of a solve that stopped on max_iters: this rank's slices of x, r and p, the scalars (bb, rr, beta), the
+ * iteration count and the residual history, one file per rank (the caller names it).  lamcg_checkpoint_load puts that
+ * state back into a handle that holds the same system with the same rank layout and element type (checked:
+ * LAMCG_ERR_SHAPE); lamcg_solve_resume then carries on bit-identically to an uninterrupted solve. */
+int lamcg_checkpoint_save(lamcg_t *h, const char *path);
+int lamcg_checkpoint_load(lamcg_t *h, const char *path);
 /* sqrt(rr/bb) after each executed iteration of the last solve; returns the count copied. */
 int lamcg_get_residual_history(lamcg_t *h, double *out, int capacity);
 /* This rank's slice of x (local_rows doubles, host pointer). */

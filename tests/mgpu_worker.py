@@ -101,8 +101,48 @@ def main():
             return oracle.cg_solve(A, b, 1000, 1e-9)
         return mk
 
+    def case_resume(name, n, k, m, loop_mode, tmpdir):
+        """solve(k) + resume(m) and solve(k) -> per-rank checkpoint files -> fresh handles -> resume(m) must both be
+        bit-identical to solve(k + m) on every rank (the deferred p update is a peer store / an all-gather here)."""
+        nonlocal ok
+        ck = os.path.join(tmpdir, f"{comm}_{name}.ckpt.rank{rank}of{world}")
+        s = lamcg_b200.Solver(local, rank, world)
+        lamcg_b200.launch.bootstrap_comm(s, n=n, mode=comm, dist=dist)
+        s.set_option("loop_mode", loop_mode)
+        s.generate_matrix(n, n)
+        s.generate_rhs()
+        full = s.solve(k + m, 1e-9)
+        x_full, h_full = s.solution(), s.residual_history()
+        s.solve(k, 1e-9)
+        s.checkpoint_save(ck)
+        res = s.solve_resume(m, 1e-9)
+        x_res, h_res = s.solution(), s.residual_history()
+        s.close()
+        dist.barrier()
+        t = lamcg_b200.Solver(local, rank, world)
+        lamcg_b200.launch.bootstrap_comm(t, n=n, mode=comm, dist=dist)
+        t.set_option("loop_mode", loop_mode)
+        t.generate_matrix(n, n)
+        t.generate_rhs()
+        t.checkpoint_load(ck)
+        res2 = t.solve_resume(m, 1e-9)
+        x_ck = t.solution()
+        t.close()
+        os.unlink(ck)
+        ref = oracle.cg_solve_generated(n, k + m, 1e-9)
+        entry = {"name": name, "n": n, "k": k, "m": m, "iters": res.iterations, "oracle_iters": ref.iters, "x_err": rel_l2(x_full, ref.x),
+                 "resume_identical": bool(np.array_equal(x_res, x_full) and np.array_equal(h_res, h_full) and res.iterations == full.iterations),
+                 "checkpoint_identical": bool(np.array_equal(x_ck, x_full) and res2.iterations == full.iterations
+                                              and res2.rel_residual == full.rel_residual)}
+        good = entry["resume_identical"] and entry["checkpoint_identical"] and entry["x_err"] <= 1e-12 and res.iterations == ref.iters
+        entry["ok"] = bool(good)
+        ok = ok and good
+        report["cases"].append(entry)
+
     import tempfile
     tmpdir = os.environ.get("LAMCG_TEST_TMP") or tempfile.gettempdir()
+    case_resume("resume_odd", 10007, 37, 64, 2, tmpdir)       # odd k: one plain step before the graph chunks
+    case_resume("resume_even_stream", 6000, 20, 21, 1, tmpdir)
     case("spd_from_files", 1500, spd_files(1500, 5, tmpdir), 1000, 2, 1e-9)
     case("gen_even", 4096, gen(4096, 300), 300, 2, 1e-12)
     case("gen_remainder", 10007, gen(10007, 200), 200, 1, 1e-12)      # n % P != 0: last rank owns the remainder
