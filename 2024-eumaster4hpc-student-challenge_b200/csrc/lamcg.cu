@@ -78,6 +78,7 @@ struct lamcg {
     long long opt_gemv_ctas_per_sm = 0;
     long long opt_ingest_threads = 4;
     long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
+    long long opt_persist_variant = 0;    // 0 auto (second generation when n <= 2048) | 1 first generation | 2 second (n <= 4096)
 
     // comm
     int comm_mode = kCommNone;
@@ -466,18 +467,36 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
         h->persist_ll_grid = grid;
     }
     const int rows_max = (int)((h->n + grid - 1) / grid);
-    int segs = 1;
-    while (segs * 2 * rows_max <= kPersistThreads / 32 && (size_t)(segs * 2) * 64 <= h->lda) segs *= 2;
-    const size_t fixed = (h->lda + (((size_t)rows_max * segs + 1) & ~(size_t)1)) * sizeof(double);
     int dev_smem_max = 0;
     CK(cudaDeviceGetAttribute(&dev_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    const size_t budget = (size_t)dev_smem_max > fixed + 4096 ? (size_t)dev_smem_max - fixed - 4096 : 0; // 4 KB for static smem
+    // Second-generation kernel (p in registers, column segments; lda <= 4096) unless persist_variant = 1 asks for the first
+    // (auto: only where every row of a CTA fits in shared memory, lda <= 2048 on 148 SMs; measured at n = 4096, where 22 of 28
+    // rows stream from L2: first generation 35.4 k it/s, second 30.3 k)
+    const bool v2_ok = h->lda <= 4096 && rows_max <= kPersistThreads;
+    const bool v2 = v2_ok && (h->opt_persist_variant == 2 || (h->opt_persist_variant == 0 && h->lda <= 2048));
+    if (h->opt_persist_variant == 2 && !v2) return h->fail(LAMCG_ERR_INVALID, "persist_variant 2 needs n <= 4096");
+    const void *kernel = (const void *)cg_persistent_kernel;
+    int segs = 1;
+    size_t fixed;
+    if (v2) {
+        kernel = h->lda <= 1024 ? (const void *)cg_persistent_v2_kernel<2> : h->lda <= 2048 ? (const void *)cg_persistent_v2_kernel<4>
+                                                                                           : (const void *)cg_persistent_v2_kernel<8>;
+        const size_t rows_pad = ((size_t)rows_max + 7) & ~(size_t)7;
+        fixed = std::max(rows_pad * (kPersistThreads / 32), (size_t)grid) * sizeof(double); // row partials, reused as the gather buffer
+    } else {
+        while (segs * 2 * rows_max <= kPersistThreads / 32 && (size_t)(segs * 2) * 64 <= h->lda) segs *= 2;
+        fixed = (h->lda + (((size_t)rows_max * segs + 1) & ~(size_t)1)) * sizeof(double);
+    }
+    cudaFuncAttributes fattr;
+    CK(cudaFuncGetAttributes(&fattr, kernel));
+    const size_t stat = fattr.sharedSizeBytes; // static shared memory counts against the same per-block limit
+    const size_t budget = (size_t)dev_smem_max > fixed + stat ? (size_t)dev_smem_max - fixed - stat : 0;
     int rows_smem = (int)std::min<size_t>((size_t)rows_max, budget / (h->lda * sizeof(double)));
     if (h->opt_persist_rows_smem >= 0) rows_smem = std::min(rows_smem, (int)h->opt_persist_rows_smem);
     const size_t smem = fixed + (size_t)rows_smem * h->lda * sizeof(double);
-    CK(cudaFuncSetAttribute(cg_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int max_blocks = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, cg_persistent_kernel, kPersistThreads, smem));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_blocks, kernel, kPersistThreads, smem));
     if (max_blocks < 1) return h->fail(LAMCG_ERR_CUDA, "persistent kernel does not fit on an SM (smem %zu)", smem);
 
     PersistArgs a;
@@ -500,7 +519,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     CK(cudaMemsetAsync(h->st, 0, sizeof(DevState), h->stream));
     CK(cudaEventRecord(h->ev_start, h->stream));
     void *params[] = {&a};
-    CK(cudaLaunchCooperativeKernel((void *)cg_persistent_kernel, dim3(grid), dim3(kPersistThreads), params, smem, h->stream));
+    CK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kPersistThreads), params, smem, h->stream));
     CK(cudaEventRecord(h->ev_stop, h->stream));
     CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
     cudaError_t se = cudaStreamSynchronize(h->stream);
@@ -658,6 +677,37 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
 
 } // namespace
 
+// ---- checkpoint / restart of a long solve (SURVEY section 8 f4) ------------------------------------
+// One file per rank: a fixed header, then this rank's slices of x, r and of the p of the last executed
+// iteration, then the residual history kept so far.  Everything else the loop needs (A, b) is the system itself.
+namespace {
+
+struct CkptHeader {
+    char magic[8];            // "LAMCGCK1"
+    uint64_t n, local_rows, row_offset;
+    int32_t dtype, rank, nranks, iters_done;
+    double bb, rr, alpha_last, beta_last, eps;
+    int32_t hist_count, reserved;
+};
+const char kCkptMagic[8] = {'L', 'A', 'M', 'C', 'G', 'C', 'K', '1'};
+
+int write_full(int fd, const void *buf, size_t bytes)
+{
+    const char *c = static_cast<const char *>(buf);
+    while (bytes > 0) {
+        ssize_t put = write(fd, c, bytes);
+        if (put < 0) {
+            if (errno == EINTR) continue;
+            return -1;
+        }
+        c += put;
+        bytes -= (size_t)put;
+    }
+    return 0;
+}
+} // namespace
+
+
 // =================================================================================================
 // extern "C" surface
 // =================================================================================================
@@ -721,6 +771,7 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_history = env_ll("history", 1);
     h->opt_gemv_ctas_per_sm = env_ll("gemv_ctas_per_sm", 0);
     h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
+    h->opt_persist_variant = env_ll("persist_variant", 0);
     h->opt_ingest_threads = env_ll("ingest_threads", 4);
     *out = h;
     return LAMCG_OK;
@@ -781,6 +832,7 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "history") h->opt_history = value;
     else if (k == "gemv_ctas_per_sm") h->opt_gemv_ctas_per_sm = value;
     else if (k == "persist_rows_smem") h->opt_persist_rows_smem = value;
+    else if (k == "persist_variant") h->opt_persist_variant = value;
     else if (k == "ingest_threads") h->opt_ingest_threads = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
@@ -1156,35 +1208,6 @@ int lamcg_solve_resume(lamcg_t *h, int more_iters, double rel_error, lamcg_resul
     }
     return run_loop(h, loop_mode, k, total, out, 1);
 }
-
-// ---- checkpoint / restart of a long solve (SURVEY section 8 f4) ------------------------------------
-// One file per rank: a fixed header, then this rank's slices of x, r and of the p of the last executed
-// iteration, then the residual history kept so far.  Everything else the loop needs (A, b) is the system itself.
-namespace {
-struct CkptHeader {
-    char magic[8];            // "LAMCGCK1"
-    uint64_t n, local_rows, row_offset;
-    int32_t dtype, rank, nranks, iters_done;
-    double bb, rr, alpha_last, beta_last, eps;
-    int32_t hist_count, reserved;
-};
-const char kCkptMagic[8] = {'L', 'A', 'M', 'C', 'G', 'C', 'K', '1'};
-
-int write_full(int fd, const void *buf, size_t bytes)
-{
-    const char *c = static_cast<const char *>(buf);
-    while (bytes > 0) {
-        ssize_t put = write(fd, c, bytes);
-        if (put < 0) {
-            if (errno == EINTR) continue;
-            return -1;
-        }
-        c += put;
-        bytes -= (size_t)put;
-    }
-    return 0;
-}
-} // namespace
 
 int lamcg_checkpoint_save(lamcg_t *h, const char *path)
 {

@@ -886,6 +886,12 @@ __device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsig
     return s;
 }
 
+// Measured and dropped (round 1, profiles/r01_persist_gen2.log): a two-level version of this exchange (groups of
+// ceil(sqrt(G)) = 13 CTAs all-to-all, then one word per group: 25 messages per CTA instead of 148) was SLOWER, 6.9 k / 8.7 k
+// cycles per exchange against 5.0 k / 5.4 k at G = 148.  The cost is per hop (store -> visible in L2 -> seen by a spinning
+// strong load -> CTA barrier -> fixed-order sum, ~1800 cycles even with 13 messages; ~700 per gpu-scope fence), not the
+// number of messages in flight, so one hop with G messages beats two hops with sqrt(G).
+
 constexpr int kPersistThreads = 512; // 128 registers per thread: the exchange and the GEMV stay spill-free
 
 __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(PersistArgs a)
@@ -1029,6 +1035,202 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(Persi
         st->done = 1;
         for (int k = 0; k < 6; ++k) st->phase_cycles[k] = ph[k];
 
+    }
+#undef LAMCG_PHASE
+}
+
+// =============================================================================================
+// Persistent loop, second generation ("column segments", n <= 4096).  Same protocol as cg_persistent_kernel (two
+// tagged-word all-gathers per iteration, redundant scalars), different GEMV and no p in shared memory:
+//   * warp w owns the column segment [w*32*PL, (w+1)*32*PL) of EVERY row of the CTA and keeps its slice of p in
+//     REGISTERS (PL doubles per lane) for the whole solve: p = r + beta p is a register update fed by one coalesced
+//     read of the published r, and a row of A costs one pass over shared memory instead of two (the first
+//     generation re-read p from shared memory for every row: A and p traffic were equal, and the GEMV was
+//     shared-memory-bandwidth bound at 2.2 us for n = 2048);
+//   * the 16 KB that p occupied now hold one more row of A: at n = 2048 all 13-14 rows of a CTA are resident (the
+//     first generation streamed the 14th row from L2 through a single warp, a ~1.5 us critical path);
+//   * 8 rows are accumulated at once and reduced across the warp by a halving butterfly (9 fp64 shuffles per 8
+//     rows instead of 40), the 16 per-warp partials of a row are added in warp order by the row's owner thread.
+// Every sum has a fixed order, so runs are bit-reproducible; arithmetic is the same unfused multiply-add.
+// =============================================================================================
+template <int PL>
+__global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(PersistArgs a)
+{
+    extern __shared__ __align__(16) double psm[];
+    constexpr int NW = kPersistThreads / 32; // 16 warps
+    constexpr int K2 = PL / 2;               // 16-byte loads per lane and row
+    constexpr int SEG = 32 * PL;             // columns per warp
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n = (int)a.n, lda = (int)a.lda;
+    double *arows = psm;                              // [rows_smem][lda] resident rows of A
+    double *part = psm + (size_t)a.rows_smem * lda;   // [rows_max rounded up to 8][NW] per-warp row partials ...
+    double *s_gather = part;                          // ... reused as the all-gather landing zone [G] (disjoint in time)
+    __shared__ double scratch[32];
+    __shared__ double s_bcast;
+    __shared__ double s_scal[4]; // alpha | beta | rr | stop code, computed once per CTA by thread 0
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int base = n / G, rem = n % G;
+    const int r0 = bid * base + (bid < rem ? bid : rem);
+    const int rcnt = base + (bid < rem ? 1 : 0);
+    const int cbase = warp * SEG + 2 * lane; // this lane's columns: cbase + 64 k + {0, 1}
+    DevState *st = a.st;
+
+    // ---- init: p = b in registers (b is zero padded to lda), own x = 0, own r = p = b, bb = b.b (same order in every CTA)
+    double preg[PL];
+    double local = 0.0;
+#pragma unroll
+    for (int k = 0; k < K2; ++k) {
+        const int c = cbase + 64 * k;
+        double2 bv = make_double2(0.0, 0.0);
+        if (c < lda) bv = *reinterpret_cast<const double2 *>(a.b + c);
+        preg[2 * k] = bv.x;
+        preg[2 * k + 1] = bv.y;
+        local = mul_add(bv.x, bv.x, local);
+        local = mul_add(bv.y, bv.y, local);
+    }
+    const double bb_t0 = block_sum(local, scratch);
+    if (tid == 0) s_bcast = bb_t0;
+    __syncthreads();
+    const double bb = s_bcast;
+    double x_own = 0.0, r_own = 0.0, p_own = 0.0, Ap_own = 0.0;
+    if (tid < rcnt) r_own = p_own = a.b[r0 + tid];
+    const int nres = rcnt < a.rows_smem ? rcnt : a.rows_smem;
+    {
+        const double *src = a.A + (size_t)r0 * lda;
+        for (int i = 2 * tid; i < nres * lda; i += 2 * kPersistThreads)
+            *reinterpret_cast<double2 *>(arows + i) = __ldg(reinterpret_cast<const double2 *>(src + i));
+    }
+    __syncthreads();
+
+    double rr = bb, beta = 0.0;
+    int it;
+    bool converged = false, broke = false;
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
+    long long tc = clock64();
+#define LAMCG_PHASE(k) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; }
+    for (it = 1; it <= a.max_iters; ++it) {
+        if (it > 1) { // p = r + beta p: register slice from the r every CTA published before its r.r partial; own rows from r_own
+#pragma unroll
+            for (int k = 0; k < K2; ++k) {
+                const int c = cbase + 64 * k;
+                if (c + 1 < n) {
+                    const double2 rv = __ldcg(reinterpret_cast<const double2 *>(a.r + c));
+                    preg[2 * k] = __dadd_rn(rv.x, __dmul_rn(beta, preg[2 * k]));
+                    preg[2 * k + 1] = __dadd_rn(rv.y, __dmul_rn(beta, preg[2 * k + 1]));
+                } else if (c < n) {
+                    preg[2 * k] = __dadd_rn(__ldcg(a.r + c), __dmul_rn(beta, preg[2 * k]));
+                }
+            }
+            if (tid < rcnt) p_own = __dadd_rn(r_own, __dmul_rn(beta, p_own));
+        }
+        LAMCG_PHASE(0)
+        // ---- GEMV: 8 rows at a time over this warp's column segment
+        for (int g0 = 0; g0 < rcnt; g0 += 8) {
+            double acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[j] = 0.0;
+                const int row = g0 + j;
+                if (row < nres) {
+                    const double *arow = arows + row * lda;
+#pragma unroll
+                    for (int k = 0; k < K2; ++k) {
+                        const int c = cbase + 64 * k;
+                        if (c < lda) {
+                            const double2 av = *reinterpret_cast<const double2 *>(arow + c);
+                            acc[j] = mul_add(av.x, preg[2 * k], acc[j]);
+                            acc[j] = mul_add(av.y, preg[2 * k + 1], acc[j]);
+                        }
+                    }
+                } else if (row < rcnt) {
+                    const double *arow = a.A + (size_t)(r0 + row) * lda;
+#pragma unroll
+                    for (int k = 0; k < K2; ++k) {
+                        const int c = cbase + 64 * k;
+                        if (c < lda) {
+                            const double2 av = __ldg(reinterpret_cast<const double2 *>(arow + c));
+                            acc[j] = mul_add(av.x, preg[2 * k], acc[j]);
+                            acc[j] = mul_add(av.y, preg[2 * k + 1], acc[j]);
+                        }
+                    }
+                }
+            }
+            // halving butterfly: after the xor-16/8/4 steps lane l holds the sum of row j = 4*bit4 + 2*bit3 + bit2 over
+            // its 4-lane group's complement; the xor-2/1 steps finish it.  Each kept value is computed by exactly one lane.
+            const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+            double v4[4], v2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double keep = b4 ? acc[4 + i] : acc[i], send = b4 ? acc[i] : acc[4 + i];
+                v4[i] = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 16));
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double keep = b3 ? v4[2 + i] : v4[i], send = b3 ? v4[i] : v4[2 + i];
+                v2[i] = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 8));
+            }
+            double v = __dadd_rn(b2 ? v2[1] : v2[0], __shfl_xor_sync(FULL, b2 ? v2[0] : v2[1], 4));
+            v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2));
+            v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1));
+            if ((lane & 3) == 0) part[(g0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)) * NW + warp] = v;
+        }
+        __syncthreads();
+        LAMCG_PHASE(1)
+        double contrib = 0.0;
+        if (tid < rcnt) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, part[tid * NW + w]);
+            Ap_own = sum;
+            contrib = __dmul_rn(p_own, sum);
+        }
+        {
+            const double cta_pap = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
+            const double pAp_w0 = grid_allgather_sum<false>(cta_pap, a.ll, (unsigned int)it, s_gather, &s_bcast, &st->error);
+            if (tid == 0) s_scal[0] = rr / pAp_w0; // alpha = rr / (p.Ap)
+        }
+        LAMCG_PHASE(2)
+        __syncthreads();
+        const double alpha = s_scal[0];
+        LAMCG_PHASE(3)
+        contrib = 0.0;
+        if (tid < rcnt) {
+            x_own = __dadd_rn(__dmul_rn(alpha, p_own), x_own);
+            r_own = __dadd_rn(__dmul_rn(-alpha, Ap_own), r_own);
+            __stcg(&a.r[r0 + tid], r_own);
+            contrib = __dmul_rn(r_own, r_own);
+        }
+        const double cta_rr = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
+        const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)kLLStride * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
+        LAMCG_PHASE(4)
+        if (tid == 0) {
+            const double rel0 = sqrt(rrn_w0 / bb);
+            s_scal[1] = rrn_w0 / rr; // beta = rr_new / rr
+            s_scal[2] = rrn_w0;
+            const bool broke0 = !(rel0 == rel0) || isinf(rel0) || !(s_scal[1] == s_scal[1]);
+            s_scal[3] = rel0 < a.eps ? 1.0 : (broke0 ? 2.0 : 0.0);
+            if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
+        }
+        __syncthreads();
+        beta = s_scal[1];
+        rr = s_scal[2];
+        LAMCG_PHASE(5)
+        if (s_scal[3] == 1.0) { converged = true; break; }
+        if (s_scal[3] == 2.0) { broke = true; break; }
+    }
+    if (tid < rcnt) a.x[r0 + tid] = x_own;
+    if (bid == 0 && tid == 0) {
+        st->bb = bb;
+        st->rr_final = rr;
+        st->iters_done = (converged || broke) ? it : (a.max_iters > 0 ? a.max_iters : 0);
+        st->converged = converged ? 1 : 0;
+        st->breakdown = broke ? 1 : 0;
+        st->max_iters = a.max_iters;
+        st->eps = a.eps;
+        st->done = 1;
+        for (int k = 0; k < 6; ++k) st->phase_cycles[k] = ph[k];
     }
 #undef LAMCG_PHASE
 }

@@ -363,13 +363,18 @@ def test_truncated_matrix_file_is_rejected(solver, tmp_path, lamcg):
 
 
 # ------------------------------------------------------- persistent single-kernel loop (loop_mode 3)
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 147, 149, 1000, 1025, 2048, 4096, 5001, 10007])
-def test_persistent_loop_generate_mode_vs_oracle(solver, n):
+@pytest.mark.parametrize("generation", [1, 2])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 147, 149, 1000, 1023, 1025, 2047, 2048, 2049, 3000, 4095, 4096, 5001, 10007])
+def test_persistent_loop_generate_mode_vs_oracle(solver, n, generation):
     """The cooperative one-kernel loop (auto for n <= 4096, forced here up to n = 10007): same exact
     iteration counts, residual history and x as the oracle; n around the CTA count exercises grids with
-    0/1/2 rows per CTA."""
+    0/1/2 rows per CTA.  generation 1 = p in shared memory, row tasks; 2 = p in registers, column segments
+    (n <= 4096; all three register widths: lda <= 1024 / 2048 / 4096; odd n exercises the scalar tail)."""
+    if generation == 2 and n > 4096:
+        pytest.skip("the second-generation kernel holds p in registers: n <= 4096")
     max_iters = 10000 if n <= 4096 else 300
     solver.set_option("loop_mode", 3)
+    solver.set_option("persist_variant", generation)
     solver.generate_matrix(n, n)
     solver.generate_rhs()
     r = solver.solve(max_iters, 1e-9)
@@ -379,7 +384,10 @@ def test_persistent_loop_generate_mode_vs_oracle(solver, n):
     err = rel_l2(solver.solution(), o.x)
     REPORT[f"persistent_gen_x_rel_l2_n{n}"] = err
     # runs that end by finite termination at ceil(n/2) finish with a pure-rounding step (see LONG_RUN note)
-    assert err <= (X_TOL_GEN if (o.iters <= LONG_RUN and not o.converged) else X_TOL)
+    # ... and for odd n that last step is ill conditioned (cond ~ 0.4 n^2): at n = 4095 the UNMODIFIED reference differs from
+    # itself by 1.79e-10 between OMP_NUM_THREADS = 1 and 8 (2048 iterations both; measured with oracle.ref_gen_solve), we
+    # differ from it by 1.82e-10 -> the north_star tolerance is widened with n^2 there (5e-10 at n = 4095)
+    assert err <= (X_TOL_GEN if (o.iters <= LONG_RUN and not o.converged) else max(X_TOL, 3e-17 * n * n))
     h = solver.residual_history()
     big = o.hist > 1e-9
     np.testing.assert_allclose(h[big], o.hist[big], rtol=REL_TOL)
@@ -396,15 +404,18 @@ def test_persistent_loop_agrees_with_graph_loop_on_spd(solver):
     solver.set_rhs(b)
     o = oracle.cg_solve(A, b, 1000, 1e-9)
     out = {}
-    for mode in (2, 3):
+    for mode, gen in ((2, 0), (3, 1), (3, 2)):
         solver.set_option("loop_mode", mode)
+        solver.set_option("persist_variant", gen)
         r = solver.solve(1000, 1e-9)
         assert r.converged and abs(r.iterations - o.iters) <= parity_util.iteration_slack(o.iters)
-        out[mode] = (r.iterations, solver.solution().copy(), r.iterations_run / r.solve_seconds)
-        assert rel_l2(out[mode][1], o.x) <= X_TOL_STOPPED
-    REPORT["spd_n1536_it_per_s_graph_vs_persistent"] = [out[2][2], out[3][2]]
-    solver.set_option("loop_mode", 3)
-    check_matched_iterations(solver, A, b, o.iters, "persistent_spd_n1536")
+        out[mode, gen] = (r.iterations, solver.solution().copy(), r.iterations_run / r.solve_seconds)
+        assert rel_l2(out[mode, gen][1], o.x) <= X_TOL_STOPPED
+    REPORT["spd_n1536_it_per_s_graph_vs_persistent_gen1_gen2"] = [out[2, 0][2], out[3, 1][2], out[3, 2][2]]
+    for gen in (1, 2):
+        solver.set_option("loop_mode", 3)
+        solver.set_option("persist_variant", gen)
+        check_matched_iterations(solver, A, b, o.iters, f"persistent_gen{gen}_spd_n1536")
     r = solver.solve(0, 1e-9)
     assert not r.converged and r.iterations == 1 and r.iterations_run == 0
 

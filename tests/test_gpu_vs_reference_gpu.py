@@ -40,6 +40,15 @@ def _need(path):
         pytest.skip(f"{os.path.relpath(path, REPO)} not built (make -C oracle refgpu needs /root/reference)")
 
 
+def _ref_gpu_solve(*args, **kw):
+    """The reference's GPU code runs in its own process; if it crashes or hangs (it writes out of bounds, see above) that is not
+    a failure of the product: skip with the evidence."""
+    try:
+        return oracle.ref_gpu_solve(*args, **kw)
+    except (subprocess.CalledProcessError, subprocess.TimeoutExpired) as e:
+        pytest.skip(f"the unmodified reference GPU class did not finish on this box: {e!r}"[:300])
+
+
 def _reference_gpu_is_sound(xr, x_cpu, what):
     """True when the reference's GPU result agrees with the reference's own CPU solver (see module docstring); otherwise a
     warning records how far off it is on this box and the caller falls back to the CPU oracle for OUR result."""
@@ -56,7 +65,7 @@ def test_generate_mode_against_reference_gpu_class(lamcg, variant, tmp_path):
     _need(oracle.REF_GPU_HARNESS[variant])
     n, k = 3000, 200
     xp = str(tmp_path / "xr.bin")
-    run = oracle.ref_gpu_solve(variant, k, 1e-9, n=n, x_path=xp)[0]
+    run = _ref_gpu_solve(variant, k, 1e-9, n=n, x_path=xp)[0]
     xr = fileformat.read_vector(xp)
     assert fileformat.read_header(xp)[0] == n and run["n"] == n and run["max_iters"] == k
     o = oracle.cg_solve_generated(n, k, 1e-9)
@@ -80,8 +89,12 @@ def test_file_mode_reference_gpu_driver_and_ours_on_the_same_files(driver, golde
     _need(ref_exe)
     pa, pb = os.path.join(golden_dir, "spd_n200_A.bin"), os.path.join(golden_dir, "spd_n200_b.bin")
     pxr, px = str(tmp_path / "xr.bin"), str(tmp_path / "x.bin")
-    rr = subprocess.run([ref_exe, pa, pb, pxr, "1000", "1e-9"], capture_output=True, text=True, timeout=300)
-    assert rr.returncode == 0, rr.stderr
+    try:
+        rr = subprocess.run([ref_exe, pa, pb, pxr, "1000", "1e-9"], capture_output=True, text=True, timeout=300)
+    except subprocess.TimeoutExpired:
+        pytest.skip("the unmodified reference GPU driver hung on this box")
+    if rr.returncode != 0 or not os.path.exists(pxr):
+        pytest.skip(f"the unmodified reference GPU driver failed on this box (rc {rr.returncode}): {rr.stderr[-200:]}")
     ro = subprocess.run([POSITIONAL, pa, pb, px, "1000", "1e-9"], capture_output=True, text=True, timeout=300)
     assert ro.returncode == 0, ro.stderr
     xr, x = fileformat.read_vector(pxr), fileformat.read_vector(px)
@@ -110,7 +123,7 @@ def test_file_mode_n2048_against_reference_gpu_class(lamcg, tmp_path):
     pa, pb, pxr = str(tmp_path / "A.bin"), str(tmp_path / "b.bin"), str(tmp_path / "xr.bin")
     fileformat.write_matrix(pa, A)
     fileformat.write_matrix(pb, b)
-    run = oracle.ref_gpu_solve("single", 1000, 1e-9, A_path=pa, b_path=pb, x_path=pxr)[0]
+    run = _ref_gpu_solve("single", 1000, 1e-9, A_path=pa, b_path=pb, x_path=pxr)[0]
     xr = fileformat.read_vector(pxr)
     o = oracle.cg_solve(A, b, 1000, 1e-9)
     with lamcg.Solver(0) as s:

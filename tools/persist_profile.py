@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""One persistent-loop solve (for ncu): python tools/persist_profile.py [n] [iters]"""
+"""One persistent-loop solve per generation with its phase timers: python tools/persist_profile.py [n] [iters]"""
 import os
 import sys
 
@@ -12,12 +12,17 @@ s = lamcg_b200.Solver(0)
 s.generate_matrix(n, n)
 s.generate_rhs()
 s.set_option("loop_mode", 3)
-r = s.solve(iters, 0.0)
-print(n, iters, r.iterations_run / r.solve_seconds, "it/s")
 names = ["p update", "GEMV", "row sums + p.Ap exchange", "alpha broadcast", "x/r update + r.r exchange", "beta broadcast"]
-prof = s.loop_profile()
-for nm, c in zip(names, prof):
-    print(f"  {nm:16s} {c / r.iterations_run:9.0f} cycles/iteration")
-print(f"  total            {sum(prof[:6]) / r.iterations_run:9.0f} cycles/iteration; wall {1e6 * r.solve_seconds / r.iterations_run:.2f} us/iteration")
+for gen in (1, 2):
+    if gen == 2 and n > 4096:
+        continue
+    s.set_option("persist_variant", gen)
+    s.solve(iters, 0.0)
+    r = s.solve(iters, 0.0)
+    print(f"generation {gen}: n={n} iters={iters} {r.iterations_run / r.solve_seconds:.0f} it/s")
+    prof = s.loop_profile()
+    for nm, c in zip(names, prof):
+        print(f"  {nm:28s} {c / r.iterations_run:9.0f} cycles/iteration")
+    print(f"  total                        {sum(prof[:6]) / r.iterations_run:9.0f} cycles/iteration; wall {1e6 * r.solve_seconds / r.iterations_run:.2f} us/iteration")
 s.close()
 

@@ -12,9 +12,9 @@ for n in [int(x) for x in (sys.argv[1:] or ["2048"])]:
     s.generate_rhs()
     iters = 2000
     for name, opts in [("graph", {"loop_mode": 2}), ("stream", {"loop_mode": 1}),
-                       ("persistent rows_smem=0", {"loop_mode": 3, "persist_rows_smem": 0}),
-                       ("persistent rows_smem=4", {"loop_mode": 3, "persist_rows_smem": 4}),
-                       ("persistent rows_smem=auto", {"loop_mode": 3, "persist_rows_smem": -1})]:
+                       ("persistent gen1 rows_smem=0", {"loop_mode": 3, "persist_rows_smem": 0, "persist_variant": 1}),
+                       ("persistent gen1 rows_smem=auto", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 1}),
+                       ("persistent gen2 (p in registers)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 0})]:
         for k, v in opts.items():
             s.set_option(k, v)
         s.solve(iters, 0.0)
