@@ -823,6 +823,27 @@ __device__ __forceinline__ void ld_relaxed_gpu_v2u64(const unsigned long long *p
 {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
 }
+// Acquire load: SASS is LDG.STRONG.GPU + CCTL.IVALL (an L1 invalidate), with NO memory barrier — several hundred cycles cheaper than
+// a relaxed load followed by __threadfence() (MEMBAR.SC.GPU + ERRBAR + CCTL.IVALL).
+__device__ __forceinline__ void ld_acquire_gpu_v2u64(const unsigned long long *p, unsigned long long &a, unsigned long long &b)
+{
+    asm volatile("ld.acquire.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+}
+// Tagged words only ever grow (tag in the upper half, tags increase every iteration, the inbox is zeroed before a solve), so a
+// max-reduction delivers them: resolved in L2, and the all-to-all round measured 12 % shorter than with plain strong stores
+// (tools/ll_latency.cu: 2526 vs 2858 cycles per round at G = 148).
+__device__ __forceinline__ void red_max_gpu_u64(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("red.relaxed.gpu.global.max.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Polling through the L2 atomic unit ("add 0"): in the G x G all-to-all a round measured 2240 cycles against 2526 with polling
+// loads (tools/ll_latency.cu), presumably because the request never touches L1.  Two 8-byte atomics, each half carries its tag.
+__device__ __forceinline__ void atom_poll_gpu_2xu64(unsigned long long *p, unsigned long long &a, unsigned long long &b)
+{
+    asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], 0;" : "=l"(a) : "l"(p) : "memory");
+    asm volatile("atom.relaxed.gpu.global.add.u64 %0, [%1], 0;" : "=l"(b) : "l"(p + 1) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); } // MEMBAR.ALL.GPU (not .SC)
 
 // Grid-wide "all-gather + fixed-order sum" that doubles as the grid barrier, in ONE L2 round trip.
 // Push model: CTA src stores its partial into slot [dst][src] of EVERY CTA's private inbox (thread t
@@ -853,9 +874,10 @@ __device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsig
     if (t < G) {
         const unsigned long long bits = (unsigned long long)__double_as_longlong(*s_bcast);
         unsigned long long *dst = inbox + ((size_t)t * G + blockIdx.x) * kLLStride;
-        // release: ONE fence, then a relaxed store (st.release would fence again)
-        if (kPublishes) __threadfence();
-        st_relaxed_gpu_v2u64(dst, ((unsigned long long)tag << 32) | (bits >> 32), ((unsigned long long)tag << 32) | (bits & 0xffffffffull));
+        // release: ONE acq_rel fence (after the CTA barrier above, so it covers every thread's r stores), then the relaxed deliveries
+        if (kPublishes) fence_acq_rel_gpu();
+        red_max_gpu_u64(dst, ((unsigned long long)tag << 32) | (bits >> 32));
+        red_max_gpu_u64(dst + 1, ((unsigned long long)tag << 32) | (bits & 0xffffffffull));
     }
     if (t >= kPollBase && t < kPollBase + G) {
         const int srcid = t - kPollBase;
@@ -863,7 +885,11 @@ __device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsig
         unsigned long long w0, w1;
         const long long t0 = clock64();
         for (;;) {
-            ld_relaxed_gpu_v2u64(src, w0, w1); // each 8-byte half carries its own tag, so a torn 16-byte access is harmless
+            // each 8-byte half carries its own tag, so a torn 16-byte access is harmless; acquire: the polling load itself
+            // measured at n = 2048 (profiles/r01_persist_gen2.log): acquire LOADS for the publishing exchange (4820 cycles; 5349 with
+            // acquire atomics), relaxed ATOMICS for the other one (4011 cycles; 4324 with relaxed loads)
+            if (kPublishes) ld_acquire_gpu_v2u64(src, w0, w1);
+            else atom_poll_gpu_2xu64(const_cast<unsigned long long *>(src), w0, w1);
             if ((unsigned int)(w0 >> 32) == tag && (unsigned int)(w1 >> 32) == tag) break;
             if (clock64() - t0 > 4000000000LL) {
                 *err_flag = 3;
@@ -871,7 +897,6 @@ __device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsig
                 __trap();
             }
         }
-        if (kPublishes) __threadfence(); // acquire: relaxed polling loads, then ONE fence
         s_gather[srcid] = __longlong_as_double((long long)(((w0 & 0xffffffffull) << 32) | (w1 & 0xffffffffull)));
     }
     __syncthreads();
