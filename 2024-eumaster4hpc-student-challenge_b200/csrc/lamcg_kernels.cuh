@@ -1130,23 +1130,21 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
     __syncthreads();
 
     double rr = bb, beta = 0.0;
+    double2 rnext[K2];
+#pragma unroll
+    for (int k = 0; k < K2; ++k) rnext[k] = make_double2(0.0, 0.0);
     int it;
     bool converged = false, broke = false;
     long long ph[6] = {0, 0, 0, 0, 0, 0};
     long long tc = clock64();
 #define LAMCG_PHASE(k) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; }
     for (it = 1; it <= a.max_iters; ++it) {
-        if (it > 1) { // p = r + beta p: register slice from the r every CTA published before its r.r partial; own rows from r_own
+        if (it > 1) { // p = r + beta p: register slice from the prefetched r (see the end of the loop body); own rows from r_own
 #pragma unroll
             for (int k = 0; k < K2; ++k) {
                 const int c = cbase + 64 * k;
-                if (c + 1 < n) {
-                    const double2 rv = __ldcg(reinterpret_cast<const double2 *>(a.r + c));
-                    preg[2 * k] = __dadd_rn(rv.x, __dmul_rn(beta, preg[2 * k]));
-                    preg[2 * k + 1] = __dadd_rn(rv.y, __dmul_rn(beta, preg[2 * k + 1]));
-                } else if (c < n) {
-                    preg[2 * k] = __dadd_rn(__ldcg(a.r + c), __dmul_rn(beta, preg[2 * k]));
-                }
+                if (c < n) preg[2 * k] = __dadd_rn(rnext[k].x, __dmul_rn(beta, preg[2 * k]));
+                if (c + 1 < n) preg[2 * k + 1] = __dadd_rn(rnext[k].y, __dmul_rn(beta, preg[2 * k + 1]));
             }
             if (tid < rcnt) p_own = __dadd_rn(r_own, __dmul_rn(beta, p_own));
         }
@@ -1230,6 +1228,14 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
         const double cta_rr = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
         const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)kLLStride * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
         LAMCG_PHASE(4)
+        // every CTA's r slice is visible now: start the reads the next p update needs, they do not depend on beta and their L2
+        // round trip overlaps thread 0's division / square root and the broadcast barrier
+#pragma unroll
+        for (int k = 0; k < K2; ++k) {
+            const int c = cbase + 64 * k;
+            if (c + 1 < n) rnext[k] = __ldcg(reinterpret_cast<const double2 *>(a.r + c));
+            else if (c < n) rnext[k].x = __ldcg(a.r + c);
+        }
         if (tid == 0) {
             const double rel0 = sqrt(rrn_w0 / bb);
             s_scal[1] = rrn_w0 / rr; // beta = rr_new / rr
