@@ -1577,10 +1577,10 @@ int lamcg_time_stream_read(lamcg_t *h, int warmup, int reps, double *ms_per_pass
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
     CK(cudaSetDevice(h->device));
     const long long count2 = (long long)(h->local_rows * h->lda * h->esz / 16);
-    const int grid = std::min(h->sm_count * 8, kMaxGrid);
-    for (int i = 0; i < warmup; ++i) stream_read_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double *>(h->A), count2, h->partials);
+    const int grid = std::min(h->sm_count * 2, kMaxGrid);
+    for (int i = 0; i < warmup; ++i) stream_read_kernel<<<grid, kStreamThreads, 0, h->stream>>>(reinterpret_cast<const double *>(h->A), count2, h->partials);
     CK(cudaEventRecord(h->ev_start, h->stream));
-    for (int i = 0; i < reps; ++i) stream_read_kernel<<<grid, 256, 0, h->stream>>>(reinterpret_cast<const double *>(h->A), count2, h->partials);
+    for (int i = 0; i < reps; ++i) stream_read_kernel<<<grid, kStreamThreads, 0, h->stream>>>(reinterpret_cast<const double *>(h->A), count2, h->partials);
     CK(cudaEventRecord(h->ev_stop, h->stream));
     CK(cudaGetLastError());
     std::vector<double> part(grid);

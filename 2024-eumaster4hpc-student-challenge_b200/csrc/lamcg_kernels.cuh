@@ -737,32 +737,36 @@ __global__ void __launch_bounds__(256) fill_kernel(void *v_, long long n, long l
         v[i] = i < n ? (T)value : T(0);
 }
 
-// Read-only streaming ceiling: sum of every element of the row block with 128-bit loads.  Each CTA
-// owns one contiguous segment and sweeps it with 8 independent loads per thread in flight — the
-// access pattern of the GEMV minus p, the row structure and the epilogue.
-__global__ void __launch_bounds__(256) stream_read_kernel(const double *A, long long count2, double *partials)
+// Read-only streaming ceiling: sum of every element of the row block with 128-bit loads, in the best access pattern found
+// for B200's HBM3e by tools/hbm_read_patterns.cu (profiles/r01_hbm_read_patterns.log: 97 shapes, 3.7-7.44 TB/s): 512 threads,
+// 32 independent 16-byte loads per thread in flight, the buffer cut into 4 MB chunks dealt round-robin to 2 x SMs CTAs
+// (7439 GB/s; one contiguous segment per CTA, the first version of this kernel, reaches 5.9 TB/s).  This is the control the GEMV is
+// compared with in bench.py (`roofline.read_only_stream_GBps`).
+constexpr int kStreamThreads = 512, kStreamLoads = 32;
+constexpr long long kStreamChunk16 = 4ll * 1024 * 1024 / 16; // 16-byte words per chunk
+
+__global__ void __launch_bounds__(kStreamThreads) stream_read_kernel(const double *A, long long count2, double *partials)
 {
     __shared__ double scratch[32];
     const uint64_t pol = l2_policy_evict_first();
-    const long long per = (count2 + gridDim.x - 1) / gridDim.x;
-    const long long lo = (long long)blockIdx.x * per;
-    const long long hi = lo + per < count2 ? lo + per : count2;
-    double s[8];
+    constexpr int NT = kStreamThreads, U = kStreamLoads;
+    double s = 0.0;
+    for (long long c0 = (long long)blockIdx.x * kStreamChunk16; c0 < count2; c0 += (long long)gridDim.x * kStreamChunk16) {
+        const long long c1 = c0 + kStreamChunk16 < count2 ? c0 + kStreamChunk16 : count2;
+        long long i = c0 + threadIdx.x;
+        for (; i + (long long)(U - 1) * NT < c1; i += (long long)U * NT) {
+            double2 v[U];
 #pragma unroll
-    for (int u = 0; u < 8; ++u) s[u] = 0.0;
-    long long i = lo + threadIdx.x;
-    for (; i + 7 * 256 < hi; i += 8 * 256) {
-        double2 v[8];
+            for (int u = 0; u < U; ++u) v[u] = ldg_stream_f64x2(A + 2 * (i + (long long)u * NT), pol);
 #pragma unroll
-        for (int u = 0; u < 8; ++u) v[u] = ldg_stream_f64x2(A + 2 * (i + u * 256), pol);
-#pragma unroll
-        for (int u = 0; u < 8; ++u) s[u] += v[u].x + v[u].y;
+            for (int u = 0; u < U; ++u) s += v[u].x + v[u].y;
+        }
+        for (; i < c1; i += NT) {
+            const double2 v = ldg_stream_f64x2(A + 2 * i, pol);
+            s += v.x + v.y;
+        }
     }
-    for (; i < hi; i += 256) {
-        const double2 v = ldg_stream_f64x2(A + 2 * i, pol);
-        s[0] += v.x + v.y;
-    }
-    const double cta = block_sum(((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7])), scratch);
+    const double cta = block_sum(s, scratch);
     if (threadIdx.x == 0) partials[blockIdx.x] = cta;
 }
 
