@@ -152,12 +152,12 @@ bool plan_tma(lamcg *h, GemvPlan &p, int variant)
     return cudaFuncSetAttribute(gemv_tma_kernel<RB, CB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
 }
 
-template <int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0>
+template <int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0, int RRB = 0>
 bool plan_ctarow(lamcg *h, GemvPlan &p, int variant)
 {
     p.variant = variant;
-    if (h->dtype == 0) p.kernel = gemv_ctarow_kernel<double, R, U, NT, CPS, PF>;
-    else p.kernel = gemv_ctarow_kernel<float, R, U, NT, CPS, 0>;
+    if (h->dtype == 0) p.kernel = gemv_ctarow_kernel<double, R, U, NT, CPS, PF, RRB>;
+    else p.kernel = gemv_ctarow_kernel<float, R, U, NT, CPS, 0, RRB>;
     p.block = NT;
     p.smem = 0;
     p.rows_per_pass = R;
@@ -189,7 +189,7 @@ int make_plan(lamcg *h)
     // flight is the fastest on tall blocks (7.3-7.4 TB/s at 100000 and 12500 rows); on short blocks the
     // 256-thread, 2 CTA/SM shape balances better (6.5-6.7 TB/s at 10000 rows)
     if (v == 0) v = h->local_rows >= 12000 ? 36 : 32;
-    if (h->dtype != 0 && (v < 30 || v > 39) && v != 61 && v != 62 && v != 63 && v != 65 && v != 67 && v != 68 && v != 69 && v != 70)
+    if (h->dtype != 0 && (v < 30 || v > 39) && v != 61 && v != 62 && v != 63 && v != 65 && v != 67 && v != 68 && v != 69 && v != 70 && (v < 71 || v > 74))
         return h->fail(LAMCG_ERR_INVALID, "gemv_variant %d is fp64 only (fp32 handles use the cta-rows family 30-39, 6x)", v);
     bool ok = false;
     GemvPlan p;
@@ -221,6 +221,10 @@ int make_plan(lamcg *h)
     case 68: ok = plan_ctarow<8, 4, 768, 1>(h, p, v); break;
     case 69: ok = plan_ctarow<4, 4, 512, 1>(h, p, v); break;
     case 70: ok = plan_ctarow<8, 4, 512, 1, 1>(h, p, v); break;
+    case 71: ok = plan_ctarow<8, 4, 512, 1, 0, 1>(h, p, v); break; // 7x: row groups dealt round-robin
+    case 72: ok = plan_ctarow<6, 4, 512, 1, 0, 1>(h, p, v); break;
+    case 73: ok = plan_ctarow<4, 4, 512, 1, 0, 1>(h, p, v); break;
+    case 74: ok = plan_ctarow<8, 4, 256, 2, 0, 1>(h, p, v); break;
     case 41: ok = plan_ldg<4, 4, 1>(h, p, v); break;
     case 44: ok = plan_ldg<2, 8, 1>(h, p, v); break;
     case 51: ok = plan_ldg<1, 8, 0, 3>(h, p, v); break;

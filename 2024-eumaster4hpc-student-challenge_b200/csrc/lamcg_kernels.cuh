@@ -344,7 +344,10 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs 
 // sit in registers and are reused for the R rows (p is read from L2 once per R rows); R accumulators per
 // thread are reduced across the CTA at the end of the pass.  No shared-memory staging, no mbarriers.
 // =============================================================================================
-template <typename T, int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0>
+// RRB = 1: the R-row groups are dealt to the CTAs round-robin (group bid, bid + G, ...) instead of one contiguous row range per
+// CTA, so that at any moment the whole GPU reads one compact window of the matrix (G * R rows) — the address pattern that
+// tools/hbm_read_patterns.cu found fastest for plain reads.
+template <typename T, int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0, int RRB = 0>
 __global__ void __launch_bounds__(NT, CPS) gemv_ctarow_kernel(GemvArgs g)
 {
     constexpr int E = kVecElems<T>;        // elements per 16-byte load: 2 doubles / 4 floats
@@ -363,9 +366,13 @@ __global__ void __launch_bounds__(NT, CPS) gemv_ctarow_kernel(GemvArgs g)
     const long long rcnt = base + (bid < rem ? 1 : 0);
     const uint64_t polA = l2_policy_evict_first();
     double cta_dot = 0.0;
-    for (long long pr = 0; pr < rcnt; pr += R) {
-        const int nr = rcnt - pr < R ? (int)(rcnt - pr) : R;
-        const T *arow0 = gA + (r0 + pr) * g.lda;
+    const long long ngroups = (g.rows + R - 1) / R;
+    const long long npass = RRB ? (ngroups - bid + G - 1) / G : (rcnt + R - 1) / R;
+    for (long long k = 0; k < npass; ++k) {
+        const long long rs = RRB ? (bid + k * G) * R : r0 + k * R;       // first row of this pass
+        const long long left = (RRB ? g.rows : r0 + rcnt) - rs;
+        const int nr = left < R ? (int)left : R;
+        const T *arow0 = gA + rs * g.lda;
         double acc[R];
 #pragma unroll
         for (int r = 0; r < R; ++r) acc[r] = 0.0;
@@ -439,8 +446,8 @@ __global__ void __launch_bounds__(NT, CPS) gemv_ctarow_kernel(GemvArgs g)
 #pragma unroll
                 for (int w = 0; w < NWARP; ++w) sum = __dadd_rn(sum, red[w][lane]);
                 const T stored = (T)sum;
-                gAp[r0 + pr + lane] = stored;
-                contrib = __dmul_rn((double)gp[g.row_offset + r0 + pr + lane], (double)stored);
+                gAp[rs + lane] = stored;
+                contrib = __dmul_rn((double)gp[g.row_offset + rs + lane], (double)stored);
             }
             contrib = warp_sum(contrib);
             cta_dot = __dadd_rn(cta_dot, contrib);

@@ -71,7 +71,7 @@ def solver(lamcg):
 
 
 # ------------------------------------------------------------------------------------- K1: GEMV
-VARIANTS = [1, 11, 12, 13, 14, 15, 16, 17, 18, 2, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 41, 44, 51, 52, 61, 62, 63, 65, 67, 68, 69, 70]
+VARIANTS = [1, 11, 12, 13, 14, 15, 16, 17, 18, 2, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 41, 44, 51, 52, 61, 62, 63, 65, 67, 68, 69, 70, 71, 72, 73, 74]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
