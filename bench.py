@@ -105,6 +105,12 @@ def reference_cpu_sample(n: int, iters: int, target_block_gb: float = 6.0):
         dt = time.perf_counter() - t0
         return iters / dt, {"kind": "port", "cores": oracle.num_threads(),
                             "sample": f"oracle port (structured O(n) matvec, NOT the dense stream), n={n}, {iters} iterations"}
+    # all the host threads this process may use, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1 to its ranks)
+    try:
+        ncpu = len(os.sched_getaffinity(0))
+    except AttributeError:
+        ncpu = os.cpu_count() or 1
+    oracle.ref().ref_set_threads(ncpu)
     P = max(1, int(round(8.0 * n * n / (target_block_gb * 1e9))))
     os.environ["LAMCG_SHIM_SIZE"] = str(P)
     try:
