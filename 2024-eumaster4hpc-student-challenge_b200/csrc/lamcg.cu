@@ -35,7 +35,7 @@ thread_local std::string g_create_error;
 constexpr int kVecThreads = 256;
 constexpr int kCommNone = 0, kCommNccl = 1, kCommPeer = 2;
 constexpr int kLoopAuto = 0, kLoopStream = 1, kLoopGraph = 2, kLoopPersistent = 3;
-constexpr size_t kPersistAutoMaxN = 4096;   // A (<= 134 MB) is L2-resident or nearly so: launch latency dominates
+constexpr size_t kPersistAutoMaxN = 16384;  // measured (profiles/r01_small_n_gen3.log): the one-kernel loop beats the graph loop up to here
 constexpr size_t kPersistMaxN = 16384;      // p must fit in shared memory next to the task partials
 
 struct GemvPlan {
@@ -78,7 +78,7 @@ struct lamcg {
     long long opt_gemv_ctas_per_sm = 0;
     long long opt_ingest_threads = 4;
     long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
-    long long opt_persist_variant = 0;    // 0 auto (second generation when n <= 2048) | 1 first generation | 2 second (n <= 4096)
+    long long opt_persist_variant = 0;    // 0 auto (second generation for n <= 2048, first below 4096, third from there) | 1 first | 2 second (n <= 4096) | 3 third
 
     // comm
     int comm_mode = kCommNone;
@@ -473,20 +473,28 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     const int rows_max = (int)((h->n + grid - 1) / grid);
     int dev_smem_max = 0;
     CK(cudaDeviceGetAttribute(&dev_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    // Second-generation kernel (p in registers, column segments; lda <= 4096) unless persist_variant = 1 asks for the first
-    // (auto: only where every row of a CTA fits in shared memory, lda <= 2048 on 148 SMs; measured at n = 4096, where 22 of 28
-    // rows stream from L2: first generation 35.4 k it/s, second 30.3 k)
+    // persist_variant: 0 auto | 1 first generation (row tasks) | 2 second (p in registers, all rows in shared memory; n <= 4096;
+    // auto for n <= 2048) | 3 third (K1's streaming row sweep inside the loop; auto above)
     const bool v2_ok = h->lda <= 4096 && rows_max <= kPersistThreads;
     const bool v2 = v2_ok && (h->opt_persist_variant == 2 || (h->opt_persist_variant == 0 && h->lda <= 2048));
+    // auto above lda = 2048: up to lda < 4096 the first generation still keeps a useful share of the rows in shared memory
+    // (n = 3000: 87.7 k it/s vs 72.9 k for the streaming sweep; equal at 4096), beyond that the sweep wins (n = 8192: 12.2 k vs 9.9 k)
+    const bool v3 = !v2 && rows_max <= kPersistThreads && (h->opt_persist_variant == 3 || (h->opt_persist_variant == 0 && h->lda >= 4096));
     if (h->opt_persist_variant == 2 && !v2) return h->fail(LAMCG_ERR_INVALID, "persist_variant 2 needs n <= 4096");
+    if (h->opt_persist_variant < 0 || h->opt_persist_variant > 3) return h->fail(LAMCG_ERR_INVALID, "persist_variant must be 0..3");
     const void *kernel = (const void *)cg_persistent_kernel;
     int segs = 1;
     size_t fixed;
+    bool resident_rows = true;
     if (v2) {
         kernel = h->lda <= 1024 ? (const void *)cg_persistent_v2_kernel<2> : h->lda <= 2048 ? (const void *)cg_persistent_v2_kernel<4>
                                                                                            : (const void *)cg_persistent_v2_kernel<8>;
         const size_t rows_pad = ((size_t)rows_max + 7) & ~(size_t)7;
         fixed = std::max(rows_pad * (kPersistThreads / 32), (size_t)grid) * sizeof(double); // row partials, reused as the gather buffer
+    } else if (v3) {
+        kernel = (const void *)cg_persistent_v3_kernel<8, 2>;
+        fixed = (h->lda + (((size_t)rows_max + 7) & ~(size_t)7)) * sizeof(double); // p | Ap of the CTA's rows
+        resident_rows = false;
     } else {
         while (segs * 2 * rows_max <= kPersistThreads / 32 && (size_t)(segs * 2) * 64 <= h->lda) segs *= 2;
         fixed = (h->lda + (((size_t)rows_max * segs + 1) & ~(size_t)1)) * sizeof(double);
@@ -495,7 +503,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     CK(cudaFuncGetAttributes(&fattr, kernel));
     const size_t stat = fattr.sharedSizeBytes; // static shared memory counts against the same per-block limit
     const size_t budget = (size_t)dev_smem_max > fixed + stat ? (size_t)dev_smem_max - fixed - stat : 0;
-    int rows_smem = (int)std::min<size_t>((size_t)rows_max, budget / (h->lda * sizeof(double)));
+    int rows_smem = resident_rows ? (int)std::min<size_t>((size_t)rows_max, budget / (h->lda * sizeof(double))) : 0;
     if (h->opt_persist_rows_smem >= 0) rows_smem = std::min(rows_smem, (int)h->opt_persist_rows_smem);
     const size_t smem = fixed + (size_t)rows_smem * h->lda * sizeof(double);
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

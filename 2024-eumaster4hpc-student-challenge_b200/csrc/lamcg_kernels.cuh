@@ -1277,4 +1277,167 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
 #undef LAMCG_PHASE
 }
 
+// =============================================================================================
+// Persistent loop, third generation ("streaming", 2048 < n <= 16384): the matrix no longer fits in the shared memory of
+// the 148 SMs, so the GEMV inside the one-kernel loop is K1's CTA-wide row sweep (R rows in flight, U 16-byte streaming
+// loads per row, thread and chunk; p comes from shared memory once per chunk and is reused for the R rows), fed from
+// L2 / HBM.  Against the graph loop this saves the three launches per iteration and K1's ramp-up and tail at sizes
+// where a GEMV lasts 20-120 us; against the first generation (one warp per row task) it streams at K1's rate.
+// Everything else (p in shared memory, two tagged-word all-gathers, redundant scalars, fixed summation orders) is the
+// first generation's.
+// =============================================================================================
+template <int R, int U>
+__global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v3_kernel(PersistArgs a)
+{
+    extern __shared__ __align__(16) double psm[];
+    constexpr int NT = kPersistThreads, NWARP = NT / 32;
+    constexpr int CH = NT * U * 2; // columns per chunk
+    static_assert(R <= 32, "row sums are finished by one warp");
+    const int n = (int)a.n, lda = (int)a.lda;
+    double *p = psm;            // [lda]
+    double *Ap_s = psm + lda;   // [rows_max rounded up to R]
+    __shared__ double red[NWARP][R];
+    __shared__ double scratch[32];
+    __shared__ double s_bcast;
+    __shared__ double s_gather[kPersistMaxGrid];
+    __shared__ double s_scal[4];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int base = n / G, rem = n % G;
+    const int r0 = bid * base + (bid < rem ? bid : rem);
+    const int rcnt = base + (bid < rem ? 1 : 0);
+    DevState *st = a.st;
+    // a matrix that fits in L2 should stay there between iterations; a larger one is streamed (evict-first) so that it does
+    // not push r and the exchange words out
+    const uint64_t polA = (size_t)n * lda * sizeof(double) <= (size_t)96 << 20 ? l2_policy_evict_normal() : l2_policy_evict_first();
+
+    double local = 0.0;
+    for (int i = tid; i < lda; i += NT) {
+        const double bi = a.b[i];
+        p[i] = bi;
+        local = mul_add(bi, bi, local);
+    }
+    const double bb_t0 = block_sum(local, scratch);
+    if (tid == 0) s_bcast = bb_t0;
+    __syncthreads();
+    const double bb = s_bcast;
+    double x_own = 0.0, r_own = 0.0, Ap_own = 0.0;
+    if (tid < rcnt) r_own = a.b[r0 + tid];
+
+    double rr = bb, beta = 0.0;
+    int it;
+    bool converged = false, broke = false;
+    long long ph[6] = {0, 0, 0, 0, 0, 0};
+    long long tc = clock64();
+#define LAMCG_PHASE(k) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; }
+    for (it = 1; it <= a.max_iters; ++it) {
+        if (it > 1) {
+            for (int i = tid; i < n; i += NT) p[i] = __dadd_rn(__ldcg(&a.r[i]), __dmul_rn(beta, p[i]));
+            __syncthreads();
+        }
+        LAMCG_PHASE(0)
+        for (int pr = 0; pr < rcnt; pr += R) {
+            const int nr = rcnt - pr < R ? rcnt - pr : R;
+            const double *arow0 = a.A + (size_t)(r0 + pr) * lda;
+            double acc[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = 0.0;
+            for (int c0 = 0; c0 < lda; c0 += CH) {
+                double2 pv[U];
+                bool cv[U];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const int c = c0 + 2 * tid + u * NT * 2;
+                    cv[u] = c < lda;
+                    pv[u] = cv[u] ? *reinterpret_cast<const double2 *>(p + c) : make_double2(0.0, 0.0);
+                }
+                double2 av[R][U];
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        const int c = c0 + 2 * tid + u * NT * 2;
+                        av[r][u] = (cv[u] && r < nr) ? ldg_stream_f64x2(arow0 + (size_t)r * lda + c, polA) : make_double2(0.0, 0.0);
+                    }
+                }
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+#pragma unroll
+                    for (int u = 0; u < U; ++u) {
+                        acc[r] = mul_add(av[r][u].x, pv[u].x, acc[r]);
+                        acc[r] = mul_add(av[r][u].y, pv[u].y, acc[r]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+            if (lane == 0) {
+#pragma unroll
+                for (int r = 0; r < R; ++r) red[warp][r] = acc[r];
+            }
+            __syncthreads();
+            if (warp == 0 && lane < nr) {
+                double sum = 0.0;
+#pragma unroll
+                for (int w = 0; w < NWARP; ++w) sum = __dadd_rn(sum, red[w][lane]);
+                Ap_s[pr + lane] = sum;
+            }
+            __syncthreads();
+        }
+        LAMCG_PHASE(1)
+        double contrib = 0.0;
+        if (tid < rcnt) {
+            Ap_own = Ap_s[tid];
+            contrib = __dmul_rn(p[r0 + tid], Ap_own);
+        }
+        {
+            const double cta_pap = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
+            const double pAp_w0 = grid_allgather_sum<false>(cta_pap, a.ll, (unsigned int)it, s_gather, &s_bcast, &st->error);
+            if (tid == 0) s_scal[0] = rr / pAp_w0;
+        }
+        LAMCG_PHASE(2)
+        __syncthreads();
+        const double alpha = s_scal[0];
+        LAMCG_PHASE(3)
+        contrib = 0.0;
+        if (tid < rcnt) {
+            x_own = __dadd_rn(__dmul_rn(alpha, p[r0 + tid]), x_own);
+            r_own = __dadd_rn(__dmul_rn(-alpha, Ap_own), r_own);
+            __stcg(&a.r[r0 + tid], r_own);
+            contrib = __dmul_rn(r_own, r_own);
+        }
+        const double cta_rr = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
+        const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)kLLStride * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
+        LAMCG_PHASE(4)
+        if (tid == 0) {
+            const double rel0 = sqrt(rrn_w0 / bb);
+            s_scal[1] = rrn_w0 / rr;
+            s_scal[2] = rrn_w0;
+            const bool broke0 = !(rel0 == rel0) || isinf(rel0) || !(s_scal[1] == s_scal[1]);
+            s_scal[3] = rel0 < a.eps ? 1.0 : (broke0 ? 2.0 : 0.0);
+            if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
+        }
+        __syncthreads();
+        beta = s_scal[1];
+        rr = s_scal[2];
+        LAMCG_PHASE(5)
+        if (s_scal[3] == 1.0) { converged = true; break; }
+        if (s_scal[3] == 2.0) { broke = true; break; }
+    }
+    if (tid < rcnt) a.x[r0 + tid] = x_own;
+    if (bid == 0 && tid == 0) {
+        st->bb = bb;
+        st->rr_final = rr;
+        st->iters_done = (converged || broke) ? it : (a.max_iters > 0 ? a.max_iters : 0);
+        st->converged = converged ? 1 : 0;
+        st->breakdown = broke ? 1 : 0;
+        st->max_iters = a.max_iters;
+        st->eps = a.eps;
+        st->done = 1;
+        for (int k = 0; k < 6; ++k) st->phase_cycles[k] = ph[k];
+    }
+#undef LAMCG_PHASE
+}
+
 } // namespace lamcgk

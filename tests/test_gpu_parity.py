@@ -363,13 +363,14 @@ def test_truncated_matrix_file_is_rejected(solver, tmp_path, lamcg):
 
 
 # ------------------------------------------------------- persistent single-kernel loop (loop_mode 3)
-@pytest.mark.parametrize("generation", [1, 2])
+@pytest.mark.parametrize("generation", [1, 2, 3])
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 147, 149, 1000, 1023, 1025, 2047, 2048, 2049, 3000, 4095, 4096, 5001, 10007])
 def test_persistent_loop_generate_mode_vs_oracle(solver, n, generation):
     """The cooperative one-kernel loop (auto for n <= 4096, forced here up to n = 10007): same exact
     iteration counts, residual history and x as the oracle; n around the CTA count exercises grids with
     0/1/2 rows per CTA.  generation 1 = p in shared memory, row tasks; 2 = p in registers, column segments
-    (n <= 4096; all three register widths: lda <= 1024 / 2048 / 4096; odd n exercises the scalar tail)."""
+    (n <= 4096; all three register widths: lda <= 1024 / 2048 / 4096; odd n exercises the scalar tail); 3 = K1's streaming
+    row sweep inside the loop (auto above n = 2048)."""
     if generation == 2 and n > 4096:
         pytest.skip("the second-generation kernel holds p in registers: n <= 4096")
     max_iters = 10000 if n <= 4096 else 300
@@ -404,15 +405,15 @@ def test_persistent_loop_agrees_with_graph_loop_on_spd(solver):
     solver.set_rhs(b)
     o = oracle.cg_solve(A, b, 1000, 1e-9)
     out = {}
-    for mode, gen in ((2, 0), (3, 1), (3, 2)):
+    for mode, gen in ((2, 0), (3, 1), (3, 2), (3, 3)):
         solver.set_option("loop_mode", mode)
         solver.set_option("persist_variant", gen)
         r = solver.solve(1000, 1e-9)
         assert r.converged and abs(r.iterations - o.iters) <= parity_util.iteration_slack(o.iters)
         out[mode, gen] = (r.iterations, solver.solution().copy(), r.iterations_run / r.solve_seconds)
         assert rel_l2(out[mode, gen][1], o.x) <= X_TOL_STOPPED
-    REPORT["spd_n1536_it_per_s_graph_vs_persistent_gen1_gen2"] = [out[2, 0][2], out[3, 1][2], out[3, 2][2]]
-    for gen in (1, 2):
+    REPORT["spd_n1536_it_per_s_graph_vs_persistent_gen1_gen2_gen3"] = [out[2, 0][2], out[3, 1][2], out[3, 2][2], out[3, 3][2]]
+    for gen in (1, 2, 3):
         solver.set_option("loop_mode", 3)
         solver.set_option("persist_variant", gen)
         check_matched_iterations(solver, A, b, o.iters, f"persistent_gen{gen}_spd_n1536")

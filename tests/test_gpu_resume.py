@@ -153,9 +153,12 @@ def test_resume_and_checkpoint_error_paths(lamcg, tmp_path):
 
 def test_cli_checkpoint_and_resume(tmp_path):
     """-c writes the checkpoint when -i runs out; a second process with -r continues; same solution file as one run."""
-    n = 5001   # above the auto threshold of the one-kernel loop, so all three runs use the graph loop
+    n = 5001
     one, two, ck = (str(tmp_path / f) for f in ("one.bin", "two.bin", "cg.ckpt"))
-    r = subprocess.run([GETOPT, "-s", str(n), "-i", "150", "-o", one], capture_output=True, text=True, timeout=300)
+    # the uninterrupted run would pick the one-kernel loop at this size (different summation order): pin it to the graph loop,
+    # which -c / -r use, so that the three runs can be compared bit for bit
+    r = subprocess.run([GETOPT, "-s", str(n), "-i", "150", "-o", one], capture_output=True, text=True, timeout=300,
+                       env=dict(os.environ, LAMCG_LOOP_MODE="2"))
     assert r.returncode == 0, r.stderr
     r = subprocess.run([GETOPT, "-s", str(n), "-i", "61", "-o", two, "-c", ck], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and os.path.exists(ck), r.stderr

@@ -13,7 +13,7 @@ s.generate_matrix(n, n)
 s.generate_rhs()
 s.set_option("loop_mode", 3)
 names = ["p update", "GEMV", "row sums + p.Ap exchange", "alpha broadcast", "x/r update + r.r exchange", "beta broadcast"]
-for gen in (1, 2):
+for gen in (1, 2, 3):
     if gen == 2 and n > 4096:
         continue
     s.set_option("persist_variant", gen)

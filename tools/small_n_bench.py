@@ -14,7 +14,10 @@ for n in [int(x) for x in (sys.argv[1:] or ["2048"])]:
     for name, opts in [("graph", {"loop_mode": 2}), ("stream", {"loop_mode": 1}),
                        ("persistent gen1 rows_smem=0", {"loop_mode": 3, "persist_rows_smem": 0, "persist_variant": 1}),
                        ("persistent gen1 rows_smem=auto", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 1}),
-                       ("persistent gen2 (p in registers)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 0})]:
+                       ("persistent gen2 (p in registers)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 2}),
+                       ("persistent gen3 (streaming sweep)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 3})]:
+        if n > 4096 and opts.get("persist_variant") == 2:
+            continue
         for k, v in opts.items():
             s.set_option(k, v)
         s.solve(iters, 0.0)
