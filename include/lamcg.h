@@ -137,7 +137,7 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out);
 /* Continue the last solve for up to `more_iters` further iterations, exactly as if it had been called with
  * max_iters + more_iters in the first place: x, r, p, rr and the iteration counter are still on the device, so
  * solve(k) followed by resume(m) is bit-identical to solve(k + m).  Needs a solve (stream or graph loop; set
- * loop_mode 2 for n <= 4096) that stopped on max_iters without converging, or a loaded checkpoint, and an unchanged
+ * loop_mode 2 for n <= 16384, where auto picks the one-kernel loop) that stopped on max_iters without converging, or a loaded checkpoint, and an unchanged
  * system; otherwise LAMCG_ERR_STATE.  `out` reports totals (iterations, iterations_run count from the original
  * start; solve_seconds is this call's loop time).  Collective over all ranks.  The reference has no equivalent: its
  * long generate-mode runs (n/2 iterations to converge, MPI_OMP.hpp:71-142) restart from x = 0. */
