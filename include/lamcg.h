@@ -85,9 +85,11 @@ const char *lamcg_last_error(const lamcg_t *h);
 const char *lamcg_version(void);
 
 /* ---- options (all optional; also readable from env LAMCG_<KEY>) ----------------------------- */
-/*  gemv_variant  0 auto | 1 ldg | 2 tma ring          loop_mode   0 auto | 1 stream | 2 graph | 3 persistent
+/*  gemv_variant  0 auto | 1x ldg | 2x tma ring | 3x, 6x, 7x cta-wide row sweep (default 36 / 32)
+ *  loop_mode     0 auto (single rank, fp64, n <= 16384: 3; else 2) | 1 stream | 2 graph | 3 persistent (one cooperative kernel)
+ *  persist_variant  0 auto | 1 | 2 | 3: generation of the persistent kernel (rows in shared memory / p in registers / streaming sweep)
  *  chunk_iters   iterations per graph launch          time_gemv   0/1 event-time every GEMV (stream mode)
- *  gemv_ctas_per_sm, gemv_stages  tuning overrides     history     0/1 keep sqrt(rr/bb) per iteration (default 1) */
+ *  gemv_ctas_per_sm, persist_rows_smem, ingest_threads  tuning overrides     history  0/1 keep sqrt(rr/bb) per iteration (default 1) */
 int lamcg_set_option(lamcg_t *h, const char *key, long long value);
 int lamcg_get_info(const lamcg_t *h, lamcg_info *out);
 
