@@ -1099,7 +1099,8 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
     constexpr unsigned FULL = 0xffffffffu;
     const int n = (int)a.n, lda = (int)a.lda;
     double *arows = psm;                              // [rows_smem][lda] resident rows of A
-    double *part = psm + (size_t)a.rows_smem * lda;   // [rows_max rounded up to 8][NW] per-warp row partials ...
+    double *part = psm + (size_t)a.rows_smem * lda;   // [NW][rows_max rounded up to 8] per-warp row partials (row index fastest: the
+                                                      // owner threads read consecutive words; [row][warp] cost 13 % bank conflicts, ncu) ...
     double *s_gather = part;                          // ... reused as the all-gather landing zone [G] (disjoint in time)
     __shared__ double scratch[32];
     __shared__ double s_bcast;
@@ -1111,6 +1112,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
     const int r0 = bid * base + (bid < rem ? bid : rem);
     const int rcnt = base + (bid < rem ? 1 : 0);
     const int cbase = warp * SEG + 2 * lane; // this lane's columns: cbase + 64 k + {0, 1}
+    const int rows_pad = (a.rows_max + 7) & ~7;
     DevState *st = a.st;
 
     // ---- init: p = b in registers (b is zero padded to lda), own x = 0, own r = p = b, bb = b.b (same order in every CTA)
@@ -1208,7 +1210,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
             double v = __dadd_rn(b2 ? v2[1] : v2[0], __shfl_xor_sync(FULL, b2 ? v2[0] : v2[1], 4));
             v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2));
             v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1));
-            if ((lane & 3) == 0) part[(g0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)) * NW + warp] = v;
+            if ((lane & 3) == 0) part[warp * rows_pad + g0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = v;
         }
         __syncthreads();
         LAMCG_PHASE(1)
@@ -1216,7 +1218,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
         if (tid < rcnt) {
             double sum = 0.0;
 #pragma unroll
-            for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, part[tid * NW + w]);
+            for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, part[w * rows_pad + tid]);
             Ap_own = sum;
             contrib = __dmul_rn(p_own, sum);
         }
