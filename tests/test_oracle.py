@@ -166,3 +166,20 @@ def test_live_reference_agrees_with_oracle():
     r = oracle.ref_omp_solve(A, b, 1000, 1e-9, threads=1)
     o = oracle.cg_solve(A, b, 1000, 1e-9)
     assert r.iters == o.iters and np.array_equal(r.x, o.x)
+
+
+def test_reference_gpu_harness_is_built_and_refuses_to_run_without_a_gpu():
+    """oracle/_ref/ref_gpu_{single,multi}.out (the unmodified reference GPU classes behind oracle/ref_gpu_harness.cu) exist where
+    /root/reference was available at build time, print their usage, and stop with exit code 3 when there is no CUDA device —
+    the checker has no CPU path either."""
+    import subprocess
+    import torch
+    for variant in ("single", "multi"):
+        exe = oracle.REF_GPU_HARNESS[variant]
+        if not os.path.exists(exe):
+            pytest.skip("oracle/_ref GPU harness not built (needs /root/reference)")
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert r.returncode == 64 and "usage:" in r.stderr
+        if not torch.cuda.is_available():
+            r = subprocess.run([exe, "gen", "8", "1e-9", "-", "1"], capture_output=True, text=True, timeout=60)
+            assert r.returncode == 3 and "no CUDA device" in r.stderr
