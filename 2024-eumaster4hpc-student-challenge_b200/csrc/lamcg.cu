@@ -37,6 +37,7 @@ constexpr int kCommNone = 0, kCommNccl = 1, kCommPeer = 2;
 constexpr int kLoopAuto = 0, kLoopStream = 1, kLoopGraph = 2, kLoopPersistent = 3;
 constexpr size_t kPersistAutoMaxN = 16384;  // measured (profiles/r01_small_n_gen3.log): the one-kernel loop beats the graph loop up to here
 constexpr size_t kPersistMaxN = 16384;      // p must fit in shared memory next to the task partials
+constexpr int kPersistUnavailable = 1;      // solve_persistent: the cooperative launch was refused, nothing ran
 
 struct GemvPlan {
     int variant = 0;
@@ -531,7 +532,15 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     CK(cudaMemsetAsync(h->st, 0, sizeof(DevState), h->stream));
     CK(cudaEventRecord(h->ev_start, h->stream));
     void *params[] = {&a};
-    CK(cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kPersistThreads), params, smem, h->stream));
+    // A cooperative launch needs every CTA resident at once; when the device cannot grant that (SMs held by another context, MPS
+    // limits) the caller falls back to the graph loop instead of failing the solve.  LAMCG_PERSIST_FAIL=1 simulates it (test hook).
+    cudaError_t le = env_ll("persist_fail", 0) ? cudaErrorCooperativeLaunchTooLarge
+                                               : cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kPersistThreads), params, smem, h->stream);
+    if (le != cudaSuccess) {
+        cudaGetLastError();
+        h->fail(LAMCG_ERR_CUDA, "cooperative launch of the one-kernel CG loop failed: %s", cudaGetErrorString(le));
+        return kPersistUnavailable;
+    }
     CK(cudaEventRecord(h->ev_stop, h->stream));
     CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
     cudaError_t se = cudaStreamSynchronize(h->stream);
@@ -1167,7 +1176,13 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     if (rc != LAMCG_OK) return rc;
 
     const int loop_mode = resolve_loop_mode(h);
-    if (loop_mode == kLoopPersistent) return solve_persistent(h, max_iters, rel_error, out);
+    int loop_mode_used = loop_mode;
+    if (loop_mode == kLoopPersistent) {
+        rc = solve_persistent(h, max_iters, rel_error, out);
+        if (rc != kPersistUnavailable) return rc;
+        if ((int)h->opt_loop_mode == kLoopPersistent) return LAMCG_ERR_CUDA; // asked for explicitly: report (message already set)
+        loop_mode_used = kLoopGraph;                                         // chosen by size: the graph loop does the same job
+    }
 
     InitArgs ia;
     ia.st = h->st;
@@ -1188,7 +1203,7 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     if (h->dtype == 0) init_solve_kernel<double><<<1, 1024, 0, h->stream>>>(ia);
     else init_solve_kernel<float><<<1, 1024, 0, h->stream>>>(ia);
     CK(cudaGetLastError());
-    return run_loop(h, loop_mode, 0, max_iters, out, 1);
+    return run_loop(h, loop_mode_used, 0, max_iters, out, 1);
 }
 
 int lamcg_solve_resume(lamcg_t *h, int more_iters, double rel_error, lamcg_result *out)

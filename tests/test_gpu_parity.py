@@ -438,3 +438,26 @@ def test_non_finite_systems_report_like_the_reference(solver, loop_mode):
     solver.set_rhs(np.ones(n))
     r = solver.solve(500, 1e-9)
     assert r.converged and r.numerical_breakdown == 0 and r.iterations == 32
+
+
+def test_refused_cooperative_launch_falls_back_to_the_graph_loop(solver, lamcg, monkeypatch):
+    """The one-kernel loop needs all its CTAs resident at once.  When the device refuses the cooperative launch (simulated by the
+    LAMCG_PERSIST_FAIL test hook) a solve whose loop was chosen by size runs through the graph loop with the same result; a
+    solve that asked for loop_mode 3 explicitly reports the failure."""
+    n = 1000
+    solver.generate_matrix(n, n)
+    solver.generate_rhs()
+    o = oracle.cg_solve_generated(n, 10000, 1e-9)
+    r = solver.solve(10000, 1e-9)
+    assert r.kernel_launches == 1 and r.iterations == o.iters            # auto: the one-kernel loop
+    monkeypatch.setenv("LAMCG_PERSIST_FAIL", "1")
+    r = solver.solve(10000, 1e-9)
+    assert r.kernel_launches > 1 and r.converged and r.iterations == o.iters
+    assert rel_l2(solver.solution(), o.x) <= X_TOL
+    solver.set_option("loop_mode", 3)
+    with pytest.raises(lamcg.LamcgError) as e:
+        solver.solve(10000, 1e-9)
+    assert e.value.code == -2 and "cooperative launch" in e.value.message
+    monkeypatch.delenv("LAMCG_PERSIST_FAIL")
+    r = solver.solve(10000, 1e-9)
+    assert r.kernel_launches == 1 and r.iterations == o.iters
