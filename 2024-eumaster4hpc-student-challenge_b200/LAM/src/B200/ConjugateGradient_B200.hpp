@@ -21,6 +21,8 @@
 #include <vector>
 #include <type_traits>
 
+#include <unistd.h>
+
 #include "lamcg.h"
 
 #include "../ConjugateGradient.hpp"
@@ -64,28 +66,36 @@ public:
     // Default: the fused NVLink peer-store exchange (needs the system size n up front because the
     // exchange buffers are exported before the matrix exists).  LAMCG_COMM=nccl, n == 0, or any rank
     // failing to map its peers makes ALL ranks use NCCL collectives instead.
+    // Every step is agreed over all ranks (RankWorld::all_ok) before the next collective one, so a failure on one rank makes ALL
+    // ranks give up together: afterwards ok() is false everywhere and nobody waits in a barrier for a rank that has left.
     double init_comm(RankWorld &world, size_t n = 0)
     {
-        if (!h_ || world.size() == 1) return 0.0;
+        if (world.size() == 1) return 0.0;
         const auto t0 = std::chrono::steady_clock::now();
+        auto give_up = [&]() {
+            lamcg_destroy(h_);
+            h_ = nullptr;
+            return 0.0;
+        };
+        if (!world.all_ok(h_ != nullptr)) return give_up();
         const char *mode = std::getenv("LAMCG_COMM");
         bool peer = n > 0 && !(mode && std::string(mode) == "nccl");
         if (peer) {
             unsigned char mine[LAMCG_PEER_HANDLE_BYTES] = {0};
             std::vector<unsigned char> all((size_t)world.size() * LAMCG_PEER_HANDLE_BYTES);
-            int ok = lamcg_comm_peer_export(h_, n, mine) == LAMCG_OK;
+            bool ok = lamcg_comm_peer_export(h_, n, mine) == LAMCG_OK;
             if (!ok) std::memset(mine, 0, sizeof mine);
             world.allgather(mine, sizeof mine, all.data());
-            if (ok) ok = lamcg_comm_init_peer(h_, all.data()) == LAMCG_OK;
-            std::vector<int> oks(world.size());
-            world.allgather(&ok, sizeof ok, oks.data());
-            for (int o : oks) peer = peer && o;
+            if (ok) ok = lamcg_comm_init_peer(h_, all.data()) == LAMCG_OK; // closes what it opened when it fails half way
+            peer = world.all_ok(ok);
             if (!peer) { // start over with a clean handle so no half-mapped peer state survives
                 const lamcg_info i = info();
                 if (rank_ == 0) std::fprintf(stderr, "peer exchange unavailable (%s); using NCCL\n", lamcg_last_error(h_));
                 lamcg_destroy(h_);
                 h_ = nullptr;
-                if (lamcg_create_typed(&h_, i.device, rank_, nranks_, kDtype) != LAMCG_OK) return 0.0;
+                const bool again = lamcg_create_typed(&h_, i.device, rank_, nranks_, kDtype) == LAMCG_OK;
+                if (!again) h_ = nullptr;
+                if (!world.all_ok(again)) return give_up();
             }
         }
         if (!peer) {
@@ -96,12 +106,21 @@ public:
             const int saved_stdout = dup(1);
             dup2(2, 1);
             unsigned char id[LAMCG_NCCL_ID_BYTES] = {0};
-            if (world.rank() == 0 && lamcg_comm_nccl_unique_id(id) != LAMCG_OK) std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
-            world.bcast(id, sizeof id, 0);
-            check(lamcg_comm_init_nccl(h_, id));
+            bool ok = true;
+            if (world.rank() == 0 && lamcg_comm_nccl_unique_id(id) != LAMCG_OK) {
+                std::fprintf(stderr, "%s\n", lamcg_last_error(nullptr));
+                ok = false;
+            }
+            if (world.all_ok(ok)) {
+                world.bcast(id, sizeof id, 0);
+                ok = world.all_ok(check(lamcg_comm_init_nccl(h_, id)));
+            } else {
+                ok = false;
+            }
             std::fflush(stdout);
             dup2(saved_stdout, 1);
             close(saved_stdout);
+            if (!ok) return give_up();
         }
         world.barrier();
         return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();

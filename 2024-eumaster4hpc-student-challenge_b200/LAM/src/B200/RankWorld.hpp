@@ -100,6 +100,19 @@ public:
         barrier();
     }
 
+    // true iff `mine` is true on every rank: every rank learns of a failure on any rank and they can leave together
+    // instead of one rank returning early while the others wait out the barrier timeout
+    bool all_ok(bool mine)
+    {
+        if (size_ == 1) return mine;
+        const int flag = mine ? 1 : 0;
+        int flags[kMaxRanks] = {0};
+        allgather(&flag, sizeof flag, flags);
+        for (int r = 0; r < size_; ++r)
+            if (!flags[r]) return false;
+        return true;
+    }
+
     void bcast(void *buf, size_t bytes, int root)
     {
         if (size_ == 1) return;

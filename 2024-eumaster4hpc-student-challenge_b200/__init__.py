@@ -215,21 +215,36 @@ class Solver:
     def load_rhs(self, path: str) -> None:
         self._ck(self._L.lamcg_load_rhs(self._h, os.fsencode(path)))
 
+    def _check_matrix_shape(self, shape, layout: int) -> int:
+        """layout 0: the whole (n, n) matrix; layout 1: this rank's (local_rows, n) block.  Anything else would make the
+        library's 2-D copy read past the end of the caller's buffer, so it is refused here (ValueError) before calling into C."""
+        if layout not in (0, 1):
+            raise ValueError(f"layout must be 0 (whole matrix) or 1 (this rank's row block), not {layout!r}")
+        if len(shape) != 2:
+            raise ValueError(f"A must be 2-dimensional, got shape {tuple(shape)}")
+        rows, n = int(shape[0]), int(shape[1])
+        want = n if layout == 0 else launch.partition(n, self.nranks, self.rank)[0]
+        if rows != want or n == 0:
+            raise ValueError(f"A has shape {tuple(shape)}; layout {layout} on rank {self.rank}/{self.nranks} needs ({want}, {n})")
+        return n
+
     def set_matrix(self, A, layout: int = 0) -> None:
         """A: numpy array (host) or an object with ``data_ptr()`` (torch tensor, host or device)."""
         if hasattr(A, "data_ptr"):
-            assert A.is_contiguous() and A.element_size() == np.dtype(self.np_dtype).itemsize
-            n = A.shape[1]
+            if not A.is_contiguous() or A.element_size() != np.dtype(self.np_dtype).itemsize:
+                raise ValueError("A must be contiguous and of the handle's element type")
+            n = self._check_matrix_shape(tuple(A.shape), layout)
             self._keep_A = A
             self._ck(self._L.lamcg_set_matrix(self._h, _vp(A.data_ptr()), n, layout))
         else:
             arr = _as_array(A, "A", self.np_dtype)
-            assert arr.ndim == 2
-            self._ck(self._L.lamcg_set_matrix(self._h, _vp(arr.ctypes.data), arr.shape[1], layout))
+            n = self._check_matrix_shape(arr.shape, layout)
+            self._ck(self._L.lamcg_set_matrix(self._h, _vp(arr.ctypes.data), n, layout))
 
     def set_rhs(self, b) -> None:
         if hasattr(b, "data_ptr"):
-            assert b.is_contiguous() and b.element_size() == np.dtype(self.np_dtype).itemsize
+            if not b.is_contiguous() or b.element_size() != np.dtype(self.np_dtype).itemsize:
+                raise ValueError("b must be contiguous and of the handle's element type")
             self._ck(self._L.lamcg_set_rhs(self._h, _vp(b.data_ptr()), b.numel()))
         else:
             arr = _as_array(b, "b", self.np_dtype).reshape(-1)
@@ -274,10 +289,16 @@ class Solver:
         return x[: self.info.local_rows]
 
     def solution(self, out=None) -> np.ndarray:
-        """Whole x; ``out`` may be a pinned torch tensor / numpy array of n doubles."""
+        """Whole x; ``out`` may be a pinned torch tensor / numpy array of n elements of the handle's type (host memory)."""
         n = self.info.n
         if out is None:
             out = np.zeros(n, dtype=self.np_dtype)
+        if hasattr(out, "data_ptr"):
+            size, item, contig = out.numel(), out.element_size(), out.is_contiguous()
+        else:
+            size, item, contig = out.size, out.itemsize, out.flags["C_CONTIGUOUS"]
+        if size < n or item != np.dtype(self.np_dtype).itemsize or not contig:
+            raise ValueError(f"out must be a contiguous buffer of at least n = {n} elements of {np.dtype(self.np_dtype).name}")
         ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
         self._ck(self._L.lamcg_get_solution(self._h, _vp(ptr)))
         return out

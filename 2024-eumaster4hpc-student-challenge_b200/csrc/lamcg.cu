@@ -78,6 +78,11 @@ struct lamcg {
     long long opt_gemv_variant = 0, opt_loop_mode = 0, opt_chunk_iters = 16, opt_time_gemv = 0, opt_history = 1;
     long long opt_gemv_ctas_per_sm = 0;
     long long opt_ingest_threads = 4;
+    long long opt_ingest_chunk_bytes = 32ll << 20; // staging buffer size of the file ingest (tests shrink it to force many chunks)
+    long long opt_peer_timeout_s = 600;   // bound of every peer flag wait; ranks may finish a cold-cache ingest minutes apart
+    long long opt_persist_grid = 0;       // 0: one CTA per SM; k > 0: at most k CTAs in the one-kernel loop (tests: small-device behaviour)
+    long long opt_debug_persist_fail = 0; // test hook: pretend the cooperative launch was refused
+    int clock_khz = 1965000;
     long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
     long long opt_persist_variant = 0;    // 0 auto (second generation for n <= 2048, first below 4096, third from there) | 1 first | 2 second (n <= 4096) | 3 third
 
@@ -144,21 +149,22 @@ bool plan_tma(lamcg *h, GemvPlan &p, int variant)
 {
     using Cfg = GemvTmaCfg<RB, CB, ST>;
     p.variant = variant;
-    p.kernel = gemv_tma_kernel<RB, CB, ST>;
+    p.kernel = lamcg_tmaring_kernel<RB, CB, ST>;
     p.block = Cfg::kThreads;
     p.smem = Cfg::kSmemBytes;
     p.rows_per_pass = RB;
     int per_sm = 1;
     p.grid = (int)std::min<size_t>((size_t)h->sm_count * per_sm, std::max<size_t>(1, h->local_rows));
-    return cudaFuncSetAttribute(gemv_tma_kernel<RB, CB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
+    return cudaFuncSetAttribute(lamcg_tmaring_kernel<RB, CB, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
 }
 
-template <int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0, int RRB = 0>
-bool plan_ctarow(lamcg *h, GemvPlan &p, int variant)
+template <int U, int NT, int CPS, int VB>
+bool plan_rowsweep(lamcg *h, GemvPlan &p, int variant)
 {
+    constexpr int R = 8;
     p.variant = variant;
-    if (h->dtype == 0) p.kernel = gemv_ctarow_kernel<double, R, U, NT, CPS, PF, RRB>;
-    else p.kernel = gemv_ctarow_kernel<float, R, U, NT, CPS, 0, RRB>;
+    if (h->dtype == 0) p.kernel = lamcg_rowsweep_kernel<double, R, U, NT, CPS, VB>;
+    else p.kernel = lamcg_rowsweep_kernel<float, R, U, NT, CPS, VB>;
     p.block = NT;
     p.smem = 0;
     p.rows_per_pass = R;
@@ -168,85 +174,64 @@ bool plan_ctarow(lamcg *h, GemvPlan &p, int variant)
     return true;
 }
 
-template <int R, int U, int PF = 0, int CPS = 2>
-bool plan_ldg(lamcg *h, GemvPlan &p, int variant)
+template <int R, int U, int CPS = 2>
+bool plan_warprows(lamcg *h, GemvPlan &p, int variant)
 {
     p.variant = variant;
-    p.kernel = gemv_ldg_kernel<R, U, PF, CPS>;
+    p.kernel = lamcg_warprows_tmap_kernel<R, U, CPS>;
     p.block = kLdgWarps * 32;
     p.smem = kLdgSmemBytes;
     p.rows_per_pass = kLdgWarps * R;
     int per_sm = h->opt_gemv_ctas_per_sm > 0 ? (int)h->opt_gemv_ctas_per_sm : CPS;
     size_t want = (h->local_rows + p.rows_per_pass - 1) / p.rows_per_pass;
     p.grid = (int)std::min<size_t>((size_t)h->sm_count * per_sm, std::max<size_t>(1, want));
-    return cudaFuncSetAttribute(gemv_ldg_kernel<R, U, PF, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
+    return cudaFuncSetAttribute(lamcg_warprows_tmap_kernel<R, U, CPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p.smem) == cudaSuccess;
 }
 
-// Variant ids: 1x = ldg family, 2x = tma-ring family.  0 = auto.
+// K1 shapes kept after the round-1 sweeps (profiles/r01_sweep*.log; ~40 measured-and-lost shapes were deleted in round 2):
+//   36  row sweep, 512 threads, 1 CTA/SM, 8 rows x 4 128-bit loads in flight   default for tall blocks (>= 12000 rows)
+//   32  row sweep, 256 threads, 2 CTA/SM, same loads                           default for short blocks
+//   46 / 42  the same two shapes with the sm_100 256-bit loads (8 rows x 2 loads of 32 bytes)
+//   11  warp-per-rows, p staged in shared memory by TMA bulk copies (north_star's literal design; 7.1-7.2 TB/s)
+//   2   whole A stream through a TMA bulk-copy ring (6.7-7.15 TB/s)
+// 0 = auto.
 int make_plan(lamcg *h)
 {
     int v = (int)h->opt_gemv_variant;
-    // measured on B200 (profiles/r01_sweep3-5.log): the "cta rows" kernel with 512 threads, 1 CTA/SM, 8 rows in
-    // flight is the fastest on tall blocks (7.3-7.4 TB/s at 100000 and 12500 rows); on short blocks the
-    // 256-thread, 2 CTA/SM shape balances better (6.5-6.7 TB/s at 10000 rows)
     if (v == 0) v = h->local_rows >= 12000 ? 36 : 32;
-    if (h->dtype != 0 && (v < 30 || v > 39) && v != 61 && v != 62 && v != 63 && v != 65 && v != 67 && v != 68 && v != 69 && v != 70 && (v < 71 || v > 74))
-        return h->fail(LAMCG_ERR_INVALID, "gemv_variant %d is fp64 only (fp32 handles use the cta-rows family 30-39, 6x)", v);
+    if (h->dtype != 0 && (v == 11 || v == 2))
+        return h->fail(LAMCG_ERR_INVALID, "gemv_variant %d is fp64 only (fp32 handles use the row-sweep family 32/36/42/46)", v);
     bool ok = false;
     GemvPlan p;
     switch (v) {
-    case 1: ok = plan_ldg<4, 2>(h, p, v); break;
-    case 11: ok = plan_ldg<4, 4>(h, p, v); break;
-    case 12: ok = plan_ldg<2, 4>(h, p, v); break;
-    case 13: ok = plan_ldg<8, 2>(h, p, v); break;
-    case 14: ok = plan_ldg<2, 8>(h, p, v); break;
-    case 15: ok = plan_ldg<1, 16>(h, p, v); break;
-    case 16: ok = plan_ldg<1, 8>(h, p, v); break;
-    case 17: ok = plan_ldg<4, 8>(h, p, v); break;
-    case 18: ok = plan_ldg<2, 16>(h, p, v); break;
-    case 31: ok = plan_ctarow<4>(h, p, v); break;
-    case 32: ok = plan_ctarow<8>(h, p, v); break;
-    case 33: ok = plan_ctarow<2>(h, p, v); break;
-    case 34: ok = plan_ctarow<8, 2>(h, p, v); break;
-    case 35: ok = plan_ctarow<16, 2>(h, p, v); break;
-    case 36: ok = plan_ctarow<8, 4, 512, 1>(h, p, v); break;
-    case 37: ok = plan_ctarow<8, 2, 512, 1>(h, p, v); break;
-    case 38: ok = plan_ctarow<8, 4, 128, 4>(h, p, v); break;
-    case 39: ok = plan_ctarow<12, 2>(h, p, v); break;
-    case 30: ok = plan_ctarow<16, 1>(h, p, v); break;
-    case 61: ok = plan_ctarow<8, 4, 1024, 1>(h, p, v); break;
-    case 62: ok = plan_ctarow<4, 4, 1024, 1>(h, p, v); break;
-    case 63: ok = plan_ctarow<4, 8, 512, 1>(h, p, v); break;
-    case 65: ok = plan_ctarow<16, 2, 512, 1>(h, p, v); break;
-    case 67: ok = plan_ctarow<6, 4, 512, 1>(h, p, v); break;
-    case 68: ok = plan_ctarow<8, 4, 768, 1>(h, p, v); break;
-    case 69: ok = plan_ctarow<4, 4, 512, 1>(h, p, v); break;
-    case 70: ok = plan_ctarow<8, 4, 512, 1, 1>(h, p, v); break;
-    case 71: ok = plan_ctarow<8, 4, 512, 1, 0, 1>(h, p, v); break; // 7x: row groups dealt round-robin
-    case 72: ok = plan_ctarow<6, 4, 512, 1, 0, 1>(h, p, v); break;
-    case 73: ok = plan_ctarow<4, 4, 512, 1, 0, 1>(h, p, v); break;
-    case 74: ok = plan_ctarow<8, 4, 256, 2, 0, 1>(h, p, v); break;
-    case 41: ok = plan_ldg<4, 4, 1>(h, p, v); break;
-    case 44: ok = plan_ldg<2, 8, 1>(h, p, v); break;
-    case 51: ok = plan_ldg<1, 8, 0, 3>(h, p, v); break;
-    case 52: ok = plan_ldg<2, 4, 0, 3>(h, p, v); break;
+    case 32: ok = plan_rowsweep<4, 256, 2, 16>(h, p, v); break;
+    case 36: ok = plan_rowsweep<4, 512, 1, 16>(h, p, v); break;
+    case 42: ok = plan_rowsweep<2, 256, 2, 32>(h, p, v); break;
+    case 46: ok = plan_rowsweep<2, 512, 1, 32>(h, p, v); break;
+    case 11: ok = plan_warprows<4, 4>(h, p, v); break;
     case 2: ok = plan_tma<16, 256, 6>(h, p, v); break;
-    case 21: ok = plan_tma<8, 256, 12>(h, p, v); break;
-    case 22: ok = plan_tma<32, 128, 6>(h, p, v); break;
-    case 23: ok = plan_tma<16, 512, 3>(h, p, v); break;
-    case 24: ok = plan_tma<16, 128, 12>(h, p, v); break;
-    case 25: ok = plan_tma<8, 512, 6>(h, p, v); break;
-    case 26: ok = plan_tma<16, 256, 4>(h, p, v); break;
-    case 27: ok = plan_tma<16, 256, 3>(h, p, v); break;
-    case 28: ok = plan_tma<8, 256, 8>(h, p, v); break;
-    case 29: ok = plan_tma<16, 128, 8>(h, p, v); break;
-    default: return h->fail(LAMCG_ERR_INVALID, "unknown gemv_variant %d", v);
+    default: return h->fail(LAMCG_ERR_INVALID, "unknown gemv_variant %d (32, 36, 42, 46, 11, 2)", v);
     }
     if (!ok) return h->fail(LAMCG_ERR_CUDA, "cudaFuncSetAttribute(max dynamic smem) failed for gemv variant %d: %s", v,
                             cudaGetErrorString(cudaGetLastError()));
     if (p.grid > kMaxGrid) p.grid = kMaxGrid;
     h->plan = p;
     return LAMCG_OK;
+}
+
+// Unmap every peer exchange buffer this rank has opened (also the partial set of a failed lamcg_comm_init_peer).
+void close_peer_handles(lamcg *h)
+{
+    for (int r = 0; r < kMaxRanks; ++r) {
+        if (r != h->rank && h->pv.base[r]) cudaIpcCloseMemHandle(h->pv.base[r]);
+        h->pv.base[r] = nullptr;
+    }
+}
+
+long long peer_timeout_cycles(const lamcg *h)
+{
+    const long long s = std::max<long long>(1, std::min<long long>(h->opt_peer_timeout_s, 86400));
+    return s * (long long)h->clock_khz * 1000ll;
 }
 
 void free_system(lamcg *h)
@@ -452,7 +437,7 @@ int ensure_hist(lamcg *h, int max_iters, int keep)
 
 int check_device_error(lamcg *h, const DevState &s)
 {
-    if (s.error != 0) return h->fail(LAMCG_ERR_DEVICE, "device reported fault %d (1 = mbarrier timeout, 2 = peer flag timeout)", s.error);
+    if (s.error != 0) return h->fail(LAMCG_ERR_DEVICE, "device reported fault %d (1 = mbarrier timeout, 2 = peer flag timeout: a peer rank did not reach the exchange within peer_timeout_s, 3 = exchange timeout inside the one-kernel loop)", s.error);
     return LAMCG_OK;
 }
 
@@ -463,7 +448,8 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "the persistent loop is fp64 only");
     if (h->n > kPersistMaxN) return h->fail(LAMCG_ERR_INVALID, "the persistent loop supports n <= %zu", kPersistMaxN);
 
-    const int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
+    int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
+    if (h->opt_persist_grid > 0) grid = (int)std::min<long long>(grid, h->opt_persist_grid);
     const size_t ll_words = (size_t)2 * kLLStride * grid * grid;
     if (!h->persist_ll || h->persist_ll_grid < grid) {
         cudaFree(h->persist_ll);
@@ -472,15 +458,21 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
         h->persist_ll_grid = grid;
     }
     const int rows_max = (int)((h->n + grid - 1) / grid);
+    // every generation of the kernel handles one owned row per thread (x, r, Ap of row r0 + tid): a device that offers few SMs
+    // (MIG slice, MPS limit) cannot run n near 16384 in one kernel -> the caller takes the graph loop instead
+    if (rows_max > kPersistThreads) {
+        h->fail(LAMCG_ERR_INVALID, "the one-kernel CG loop needs ceil(n / CTAs) <= %d rows per CTA (n = %zu on %d CTAs gives %d)", kPersistThreads, h->n, grid, rows_max);
+        return kPersistUnavailable;
+    }
     int dev_smem_max = 0;
     CK(cudaDeviceGetAttribute(&dev_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
     // persist_variant: 0 auto | 1 first generation (row tasks) | 2 second (p in registers, all rows in shared memory; n <= 4096;
     // auto for n <= 2048) | 3 third (K1's streaming row sweep inside the loop; auto above)
-    const bool v2_ok = h->lda <= 4096 && rows_max <= kPersistThreads;
+    const bool v2_ok = h->lda <= 4096;
     const bool v2 = v2_ok && (h->opt_persist_variant == 2 || (h->opt_persist_variant == 0 && h->lda <= 2048));
     // auto above lda = 2048: up to lda < 4096 the first generation still keeps a useful share of the rows in shared memory
     // (n = 3000: 87.7 k it/s vs 72.9 k for the streaming sweep; equal at 4096), beyond that the sweep wins (n = 8192: 12.2 k vs 9.9 k)
-    const bool v3 = !v2 && rows_max <= kPersistThreads && (h->opt_persist_variant == 3 || (h->opt_persist_variant == 0 && h->lda >= 4096));
+    const bool v3 = !v2 && (h->opt_persist_variant == 3 || (h->opt_persist_variant == 0 && h->lda >= 4096));
     if (h->opt_persist_variant == 2 && !v2) return h->fail(LAMCG_ERR_INVALID, "persist_variant 2 needs n <= 4096");
     if (h->opt_persist_variant < 0 || h->opt_persist_variant > 3) return h->fail(LAMCG_ERR_INVALID, "persist_variant must be 0..3");
     const void *kernel = (const void *)cg_persistent_kernel;
@@ -533,8 +525,8 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     CK(cudaEventRecord(h->ev_start, h->stream));
     void *params[] = {&a};
     // A cooperative launch needs every CTA resident at once; when the device cannot grant that (SMs held by another context, MPS
-    // limits) the caller falls back to the graph loop instead of failing the solve.  LAMCG_PERSIST_FAIL=1 simulates it (test hook).
-    cudaError_t le = env_ll("persist_fail", 0) ? cudaErrorCooperativeLaunchTooLarge
+    // limits) the caller falls back to the graph loop instead of failing the solve.  Option debug_persist_fail simulates it (test hook).
+    cudaError_t le = h->opt_debug_persist_fail ? cudaErrorCooperativeLaunchTooLarge
                                                : cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kPersistThreads), params, smem, h->stream);
     if (le != cudaSuccess) {
         cudaGetLastError();
@@ -776,6 +768,7 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
         return LAMCG_ERR_CUDA;
     }
     h->sm_count = prop.multiProcessorCount;
+    h->clock_khz = prop.clockRate > 0 ? prop.clockRate : 1965000;
     if ((e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking)) != cudaSuccess) return bail("cudaStreamCreate", e);
     if ((e = cudaMalloc(&h->st, sizeof(DevState))) != cudaSuccess) return bail("cudaMalloc(state)", e);
     if ((e = cudaMemset(h->st, 0, sizeof(DevState))) != cudaSuccess) return bail("cudaMemset(state)", e);
@@ -794,6 +787,9 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
     h->opt_persist_variant = env_ll("persist_variant", 0);
     h->opt_ingest_threads = env_ll("ingest_threads", 4);
+    h->opt_ingest_chunk_bytes = env_ll("ingest_chunk_bytes", 32ll << 20);
+    h->opt_peer_timeout_s = env_ll("peer_timeout_s", 600);
+    h->opt_persist_grid = env_ll("persist_grid", 0);
     *out = h;
     return LAMCG_OK;
 }
@@ -823,9 +819,7 @@ void lamcg_destroy(lamcg_t *h)
     // blocks until such graphs are gone, so the executable graph goes first.
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->nccl) nccl_api().CommDestroy(h->nccl);
-    if (h->comm_mode == kCommPeer)
-        for (int r = 0; r < h->nranks; ++r)
-            if (r != h->rank && h->pv.base[r]) cudaIpcCloseMemHandle(h->pv.base[r]);
+    close_peer_handles(h);
     cudaFree(h->peer_base);
     cudaFree(h->persist_ll);
     free_system(h);
@@ -855,6 +849,10 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "persist_rows_smem") h->opt_persist_rows_smem = value;
     else if (k == "persist_variant") h->opt_persist_variant = value;
     else if (k == "ingest_threads") h->opt_ingest_threads = value;
+    else if (k == "ingest_chunk_bytes") h->opt_ingest_chunk_bytes = value;
+    else if (k == "peer_timeout_s") { h->opt_peer_timeout_s = value; h->pv.timeout_cycles = peer_timeout_cycles(h); }
+    else if (k == "persist_grid") h->opt_persist_grid = value;
+    else if (k == "debug_persist_fail") h->opt_debug_persist_fail = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->alloc_n) {
@@ -938,6 +936,7 @@ int lamcg_comm_peer_export(lamcg_t *h, size_t n, void *handle_out)
     const size_t lda = (n + 15) / 16 * 16;
     const size_t hdr = (sizeof(PeerHeader) + 255) / 256 * 256;
     h->pv = PeerView{};
+    h->pv.timeout_cycles = peer_timeout_cycles(h);
     h->pv.off_p[0] = (long long)hdr;
     h->pv.off_p[1] = (long long)(hdr + lda * 8);   // sized for fp64; fp32 handles use the first half of each buffer
     h->pv.off_xg[0] = (long long)(hdr + 2 * lda * 8);
@@ -968,8 +967,10 @@ int lamcg_comm_init_peer(lamcg_t *h, const void *all_handles)
     for (int r = 0; r < h->nranks; ++r) {
         PeerHandleWire w;
         memcpy(&w, blob + (size_t)r * LAMCG_PEER_HANDLE_BYTES, sizeof w);
-        if (w.rank != r || w.n != h->peer_n || w.bytes != h->peer_bytes)
+        if (w.rank != r || w.n != h->peer_n || w.bytes != h->peer_bytes) {
+            close_peer_handles(h);
             return h->fail(LAMCG_ERR_COMM, "peer handle %d is inconsistent (rank %d, n %llu, bytes %llu)", r, w.rank, w.n, w.bytes);
+        }
         if (r == h->rank) {
             h->pv.base[r] = h->peer_base;
         } else {
@@ -977,6 +978,7 @@ int lamcg_comm_init_peer(lamcg_t *h, const void *all_handles)
             cudaError_t e = cudaIpcOpenMemHandle(&ptr, w.ipc, cudaIpcMemLazyEnablePeerAccess);
             if (e != cudaSuccess) {
                 cudaGetLastError();
+                close_peer_handles(h); // comm_mode stays kCommNone, so destroy would not close what was opened so far
                 return h->fail(LAMCG_ERR_COMM, "cudaIpcOpenMemHandle(rank %d) failed: %s (peer access over NVLink is required)", r,
                                cudaGetErrorString(e));
             }
@@ -1180,8 +1182,10 @@ int lamcg_solve(lamcg_t *h, int max_iters, double rel_error, lamcg_result *out)
     if (loop_mode == kLoopPersistent) {
         rc = solve_persistent(h, max_iters, rel_error, out);
         if (rc != kPersistUnavailable) return rc;
-        if ((int)h->opt_loop_mode == kLoopPersistent) return LAMCG_ERR_CUDA; // asked for explicitly: report (message already set)
-        loop_mode_used = kLoopGraph;                                         // chosen by size: the graph loop does the same job
+        if ((int)h->opt_loop_mode == kLoopPersistent) // asked for explicitly: report (message already set)
+            return h->err.find("rows per CTA") != std::string::npos ? LAMCG_ERR_INVALID : LAMCG_ERR_CUDA;
+        loop_mode_used = kLoopGraph; // chosen by size: the graph loop does the same job
+        h->err.clear();              // ... and the solve is not a failure
     }
 
     InitArgs ia;
@@ -1366,9 +1370,10 @@ int lamcg_get_solution(lamcg_t *h, void *x)
         peer_gather_wait_kernel<<<1, 32, 0, h->stream>>>(h->pv, gseq, h->st);
         CK(cudaGetLastError());
         CK(cudaMemcpyAsync(x, h->peer_base + h->pv.off_xg[buf], h->n * h->esz, cudaMemcpyDeviceToHost, h->stream));
+        CK(cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream));
         cudaError_t se = cudaStreamSynchronize(h->stream);
         if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "solution gather faulted on the device: %s", cudaGetErrorString(se));
-        return LAMCG_OK;
+        return check_device_error(h, h->h_st[2]); // 2: a peer rank never delivered its slice
     }
     if (h->comm_mode != kCommNccl) return h->fail(LAMCG_ERR_STATE, "get_solution over ranks needs an initialised communicator");
     if (h->local_rows)

@@ -31,7 +31,7 @@ struct DevState {
     int converged;
     int breakdown;     // stopped on a non-finite residual / beta
     int iters_done;
-    int error;         // 0 ok | 1 mbarrier timeout | 2 peer-flag timeout
+    int error;         // 0 ok | 1 mbarrier timeout | 2 peer-flag timeout | 3 persistent-loop exchange timeout
     int hist_cap;
     unsigned int ticket_gemv;
     unsigned int ticket_xr;
@@ -64,6 +64,7 @@ struct PeerView {
     unsigned char *base[kMaxRanks]; // exchange buffer of every rank as mapped in THIS process
     long long off_p[2];             // byte offsets of the two full-length p buffers
     long long off_xg[2];            // byte offsets of the two solution-gather buffers
+    long long timeout_cycles;       // bound of every flag wait (peer_wait_all)
     int me, nranks;
 };
 
@@ -72,6 +73,8 @@ template <typename T = double>
 __device__ __forceinline__ T *peer_p(const PeerView &pv, int r, int buf) { return reinterpret_cast<T *>(pv.base[r] + pv.off_p[buf]); }
 template <typename T = double>
 __device__ __forceinline__ T *peer_xg(const PeerView &pv, int r, int buf) { return reinterpret_cast<T *>(pv.base[r] + pv.off_xg[buf]); }
+
+__device__ __forceinline__ int ld_volatile_int(const int *p) { return *(const volatile int *)p; }
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long *p)
 {
@@ -90,23 +93,31 @@ __device__ __forceinline__ double ld_relaxed_sys_f64(const double *p)
     return v;
 }
 
-// Spin (bounded: ~30 s, then fault instead of hanging the GPU) until all nranks flags reach `seq`.
-// Called by every thread of a CTA; lanes 0..nranks-1 poll, the CTA barrier releases everybody.
-__device__ __forceinline__ void peer_wait_all(const unsigned long long *flags, int nranks, unsigned long long seq, int *err_flag)
+// Spin until all nranks flags reach `seq`.  Bounded by pv.timeout_cycles (option peer_timeout_s, default 600 s: ranks may
+// finish a cold-cache file ingest minutes apart; the NCCL path and the reference's MPI drivers would simply wait).  On timeout
+// the kernel does NOT trap (a trap poisons the CUDA context of the whole process): it records error 2, latches `done` so that
+// every later kernel of the loop is a no-op, and returns false in ALL threads; the caller leaves the kernel and the host
+// reports LAMCG_ERR_DEVICE.  Called by every thread of a CTA; lanes 0..nranks-1 poll, the CTA barrier releases everybody.
+__device__ __forceinline__ bool peer_wait_all(const unsigned long long *flags, int nranks, unsigned long long seq, DevState *st,
+                                              long long timeout_cycles)
 {
+    int failed = 0;
     if ((int)threadIdx.x < nranks) {
         const long long t0 = clock64();
         while (ld_acquire_sys_u64(&flags[threadIdx.x]) < seq) {
-            if (clock64() - t0 > 60000000000LL) {
-                *err_flag = 2;
-                __threadfence_system();
-                __trap();
+            if (clock64() - t0 > timeout_cycles || ld_volatile_int(&st->error) != 0) {
+                failed = 1;
+                break;
             }
         }
+        if (failed) {
+            st->error = 2;
+            __threadfence();
+            st->done = 1;
+        }
     }
-    __syncthreads();
+    return __syncthreads_or(failed) == 0;
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -194,58 +205,78 @@ __device__ __forceinline__ double2 ldg_stream_f64x2(const double *ptr, uint64_t 
     return v;
 }
 
-// same, asking L2 to fetch 256 bytes per miss (two adjacent 128-byte lines share a DRAM burst)
-__device__ __forceinline__ double2 ldg_stream_f64x2_pf256(const double *ptr, uint64_t policy)
-{
-    double2 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.L2::256B.v2.f64 {%0, %1}, [%2], %3;"
-                 : "=d"(v.x), "=d"(v.y)
-                 : "l"(ptr), "l"(policy));
-    return v;
-}
-
 // ---------------------------------------------------------------------------------------------
 // Element-type helpers.  The hot path is fp64 (what the reference's drivers instantiate); the <float>
 // instantiation of the reference classes is served by the same kernels with T = float for everything that
 // is STORED (A, b, x, r, p, Ap) while every reduction, alpha, beta and the stop test stay in fp64.
 // ---------------------------------------------------------------------------------------------
-template <typename T> struct Vec16;                       // one 16-byte load worth of elements
-template <> struct Vec16<double> { double v[2]; };
-template <> struct Vec16<float> { float v[4]; };
-template <typename T> constexpr int kVecElems = 16 / (int)sizeof(T);
+template <typename T, int VB> struct VecN { T v[VB / (int)sizeof(T)]; }; // one VB-byte load worth of elements (VB = 16 or 32)
 
-__device__ __forceinline__ Vec16<double> ldg_stream16(const double *ptr, uint64_t policy)
+// Streaming load of the matrix: read-only path, no L1 allocation, L2 policy hint.  VB = 32 is the 256-bit global load that
+// sm_100 added (PTX .v4.f64 / .v8.f32; SASS LDG.E.NA.ENL2.256.CONSTANT).
+template <typename T, int VB> __device__ __forceinline__ VecN<T, VB> ldg_stream_vec(const T *ptr, uint64_t policy);
+template <> __device__ __forceinline__ VecN<double, 16> ldg_stream_vec<double, 16>(const double *ptr, uint64_t policy)
 {
-    const double2 t = ldg_stream_f64x2(ptr, policy);
-    Vec16<double> r;
-    r.v[0] = t.x;
-    r.v[1] = t.y;
+    VecN<double, 16> r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.f64 {%0, %1}, [%2], %3;" : "=d"(r.v[0]), "=d"(r.v[1]) : "l"(ptr), "l"(policy));
     return r;
 }
-__device__ __forceinline__ Vec16<float> ldg_stream16(const float *ptr, uint64_t policy)
+template <> __device__ __forceinline__ VecN<double, 32> ldg_stream_vec<double, 32>(const double *ptr, uint64_t policy)
 {
-    Vec16<float> r;
+    VecN<double, 32> r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f64 {%0, %1, %2, %3}, [%4], %5;"
+                 : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3])
+                 : "l"(ptr), "l"(policy));
+    return r;
+}
+template <> __device__ __forceinline__ VecN<float, 16> ldg_stream_vec<float, 16>(const float *ptr, uint64_t policy)
+{
+    VecN<float, 16> r;
     asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;"
                  : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3])
                  : "l"(ptr), "l"(policy));
     return r;
 }
-__device__ __forceinline__ Vec16<double> ldg_vec16(const double *ptr)
+template <> __device__ __forceinline__ VecN<float, 32> ldg_stream_vec<float, 32>(const float *ptr, uint64_t policy)
+{
+    VecN<float, 32> r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(ptr), "l"(policy));
+    return r;
+}
+// p: read-only path WITH L1 allocation (every CTA re-reads it once per pass)
+template <typename T, int VB> __device__ __forceinline__ VecN<T, VB> ldg_vec(const T *ptr);
+template <> __device__ __forceinline__ VecN<double, 16> ldg_vec<double, 16>(const double *ptr)
 {
     const double2 t = __ldg(reinterpret_cast<const double2 *>(ptr));
-    Vec16<double> r;
+    VecN<double, 16> r;
     r.v[0] = t.x;
     r.v[1] = t.y;
     return r;
 }
-__device__ __forceinline__ Vec16<float> ldg_vec16(const float *ptr)
+template <> __device__ __forceinline__ VecN<double, 32> ldg_vec<double, 32>(const double *ptr)
+{
+    VecN<double, 32> r;
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(r.v[0]), "=d"(r.v[1]), "=d"(r.v[2]), "=d"(r.v[3]) : "l"(ptr));
+    return r;
+}
+template <> __device__ __forceinline__ VecN<float, 16> ldg_vec<float, 16>(const float *ptr)
 {
     const float4 t = __ldg(reinterpret_cast<const float4 *>(ptr));
-    Vec16<float> r;
+    VecN<float, 16> r;
     r.v[0] = t.x;
     r.v[1] = t.y;
     r.v[2] = t.z;
     r.v[3] = t.w;
+    return r;
+}
+template <> __device__ __forceinline__ VecN<float, 32> ldg_vec<float, 32>(const float *ptr)
+{
+    VecN<float, 32> r;
+    asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]), "=f"(r.v[7])
+                 : "l"(ptr));
     return r;
 }
 // acc + a*b in fp64: unfused like the reference for doubles; for floats the product is exact in fp64
@@ -259,8 +290,6 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
-
-__device__ __forceinline__ int ld_volatile_int(const int *p) { return *(const volatile int *)p; }
 
 // ---------------------------------------------------------------------------------------------
 // Reductions.  All sums are evaluated in a fixed order (no floating-point atomics), so a solve is

@@ -34,13 +34,15 @@ struct GemvArgs {
 // Peer mode prologue of K1: p for iteration `it` is complete once every rank's K3 of iteration it-1
 // has raised p_flag (the first iteration reads the locally initialised p = b).  Returns the sequence
 // number this iteration publishes its scalars with.  Called by all threads of the CTA.
-__device__ __forceinline__ unsigned long long gemv_peer_prologue(const GemvArgs &g)
+__device__ __forceinline__ bool gemv_peer_prologue(const GemvArgs &g, unsigned long long &seq)
 {
-    if (g.pv.nranks <= 1 || !g.check_done) return 0ull;
+    seq = 0ull;
+    if (g.pv.nranks <= 1 || !g.check_done) return true;
     const int it = g.st->iter[g.par];
     const unsigned long long base = g.st->seq_base;
-    if (it >= 1) peer_wait_all(peer_hdr(g.pv, g.pv.me)->p_flag, g.pv.nranks, base + (unsigned long long)it, &g.st->error);
-    return base + (unsigned long long)it + 1ull;
+    seq = base + (unsigned long long)it + 1ull;
+    if (it >= 1) return peer_wait_all(peer_hdr(g.pv, g.pv.me)->p_flag, g.pv.nranks, base + (unsigned long long)it, g.st, g.pv.timeout_cycles);
+    return true;
 }
 
 // =============================================================================================
@@ -68,7 +70,7 @@ struct GemvTmaCfg {
 };
 
 template <int RB, int CB, int STAGES>
-__global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_tma_kernel(GemvArgs g)
+__global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) lamcg_tmaring_kernel(GemvArgs g)
 {
     const double *gA = static_cast<const double *>(g.A), *gp = static_cast<const double *>(g.p);
     double *gAp = static_cast<double *>(g.Ap);
@@ -102,7 +104,8 @@ __global__ void __launch_bounds__(GemvTmaCfg<RB, CB, STAGES>::kThreads, 1) gemv_
         fence_mbar_init();
     }
     __syncthreads();
-    const unsigned long long seq = gemv_peer_prologue(g);
+    unsigned long long seq;
+    if (!gemv_peer_prologue(g, seq)) return; // peer flag timeout: error recorded, loop latched done
 
     if (warp == NW) {
         // ------------------------------------------------------------------ producer warp
@@ -208,8 +211,8 @@ constexpr int kLdgPChunk = 2048;
 constexpr int kLdgPStages = 3;
 constexpr size_t kLdgSmemBytes = (size_t)kLdgPStages * kLdgPChunk * 8 + 2 * kLdgPStages * 8 + kLdgWarps * 8 + 64;
 
-template <int R, int U, int PF = 0, int CPS = 2>
-__global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs g)
+template <int R, int U, int CPS = 2>
+__global__ void __launch_bounds__(kLdgWarps * 32, CPS) lamcg_warprows_tmap_kernel(GemvArgs g)
 {
     const double *gA = static_cast<const double *>(g.A), *gp = static_cast<const double *>(g.p);
     double *gAp = static_cast<double *>(g.Ap);
@@ -241,7 +244,8 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs 
         fence_mbar_init();
     }
     __syncthreads();
-    const unsigned long long seq = gemv_peer_prologue(g);
+    unsigned long long seq;
+    if (!gemv_peer_prologue(g, seq)) return; // peer flag timeout: error recorded, loop latched done
 
     const uint64_t polA = l2_policy_evict_first();
     const uint64_t polP = l2_policy_evict_last();
@@ -293,7 +297,7 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs 
                         const bool cv = cc < nc;
 #pragma unroll
                         for (int r = 0; r < R; ++r) {
-                            if (cv && r < nr) a[r][u] = PF ? ldg_stream_f64x2_pf256(arow[r] + c0 + cc, polA) : ldg_stream_f64x2(arow[r] + c0 + cc, polA);
+                            if (cv && r < nr) a[r][u] = ldg_stream_f64x2(arow[r] + c0 + cc, polA);
                             else a[r][u] = make_double2(0.0, 0.0);
                         }
                         pv[u] = cv ? *reinterpret_cast<const double2 *>(pb + cc) : make_double2(0.0, 0.0);
@@ -338,122 +342,150 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) gemv_ldg_kernel(GemvArgs 
 }
 
 // =============================================================================================
-// K1, variant 3 ("cta rows"): the whole CTA sweeps one row at a time, R rows in flight.
-// Thread t owns columns {2t, 2t+1} + 512k of every 2048-column chunk: one CTA-wide load instruction covers
-// 4 KB of contiguous row, a chunk of one row is 16 KB contiguous.  The thread's 4 double2 of p for the chunk
-// sit in registers and are reused for the R rows (p is read from L2 once per R rows); R accumulators per
-// thread are reduced across the CTA at the end of the pass.  No shared-memory staging, no mbarriers.
+// K1, default ("cta rows"): the whole CTA sweeps one row at a time, R rows in flight.
+// Thread t owns E = VB/sizeof(T) consecutive columns out of every NT*E of a CH = NT*U*E column chunk: one CTA-wide load
+// instruction covers NT*VB bytes of contiguous row (8 KB with 512 threads and 128-bit loads, 16 KB with the sm_100 256-bit
+// form), a chunk of one row is U of those.  The thread's U vectors of p for the chunk sit in registers and are reused for the R
+// rows (p is read from L2 once per R rows); R accumulators per thread are reduced across the CTA at the end of the pass.
+// No shared-memory staging, no mbarriers.
+// Rows are dealt to the CTAs as balanced contiguous ranges (they differ by at most one row).  A CTA's range is swept in full
+// R-row passes; the remaining rows (< R) go through passes of 4, 2 and 1 rows with proportionally MORE loads per row, so every
+// pass keeps the same R*U vector loads in flight per thread: at 12500 rows per GPU (n = 100000 on 8 GPUs, 84-85 rows per CTA)
+// a plain "8 rows, 4 of them masked" last pass ran with half the bytes in flight for ~1/11 of the kernel.
 // =============================================================================================
-// RRB = 1: the R-row groups are dealt to the CTAs round-robin (group bid, bid + G, ...) instead of one contiguous row range per
-// CTA, so that at any moment the whole GPU reads one compact window of the matrix (G * R rows) — the address pattern that
-// tools/hbm_read_patterns.cu found fastest for plain reads.
-template <typename T, int R, int U = 4, int NT = 256, int CPS = 2, int PF = 0, int RRB = 0>
-__global__ void __launch_bounds__(NT, CPS) gemv_ctarow_kernel(GemvArgs g)
+constexpr int kCtaRowMaxR = 8;
+struct kTrue { static constexpr bool value = true; };
+struct kFalse { static constexpr bool value = false; };
+
+// One pass: R rows starting at arow0 (row stride lda), all lda columns.  Returns (warp 0, all lanes) the sum over the R rows of
+// p[row] * Ap[row]; 0.0 in the other warps.  red: [NT/32][kCtaRowMaxR] shared scratch.
+template <typename T, int R, int U, int NT, int VB>
+__device__ __forceinline__ double ctarow_pass(const T *__restrict__ arow0, const T *__restrict__ gp, T *__restrict__ Ap_rs,
+                                              const T *__restrict__ p_rs, long long lda, uint64_t polA,
+                                              double (*red)[kCtaRowMaxR])
 {
-    constexpr int E = kVecElems<T>;        // elements per 16-byte load: 2 doubles / 4 floats
-    constexpr int CH = NT * U * E;         // columns per chunk (4096 doubles for the default shape)
+    constexpr int E = VB / (int)sizeof(T); // elements per load
+    constexpr int CH = NT * U * E;         // columns per chunk
     constexpr int NWARP = NT / 32;
-    static_assert(R <= 32, "row sums are finished by one warp");
-    __shared__ double red[NWARP][R];
+    static_assert(R <= kCtaRowMaxR, "row sums are finished by one warp from red[][kCtaRowMaxR]");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = 0.0;
+    // One chunk: U vectors of p, then R*U streaming loads of A issued back to back, then the products.  Row r is addressed
+    // as (row r-1) + lda by pointer increments and the U loads of a row by immediate offsets, so the full-chunk loop below
+    // is loads + 2 integer adds per row (the first version recomputed (row)*lda in 64 bits per load under a predicate:
+    // 527 instructions per chunk for 36 loads, profiles/r02_sass_k1_summary.txt).
+    auto chunk = [&](const T *__restrict__ pa, const T *__restrict__ pp, auto pred, long long c_first) {
+        constexpr bool kPred = decltype(pred)::value;
+        VecN<T, VB> pv[U];
+        bool cv[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            cv[u] = !kPred || c_first + (long long)u * NT * E < lda; // lda % 16 == 0 and E <= 8: a vector is all in or all out
+            if (cv[u]) pv[u] = ldg_vec<T, VB>(pp + u * NT * E);
+            else {
+#pragma unroll
+                for (int e = 0; e < E; ++e) pv[u].v[e] = T(0);
+            }
+        }
+        VecN<T, VB> a[R][U];
+        const T *pr = pa;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (cv[u]) a[r][u] = ldg_stream_vec<T, VB>(pr + u * NT * E, polA);
+                else {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) a[r][u].v[e] = T(0);
+                }
+            }
+            pr += lda;
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if constexpr (sizeof(T) == 4) {
+                // fp32 storage: the U*E products of this thread's slice of the chunk are summed in fp32 (unfused, like the
+                // reference's float loop, but only U*E terms deep), then folded into the fp64 accumulator once per chunk:
+                // converting every product to fp64 made the kernel FP64-pipe bound (same 10.9 ms as the fp64 sweep for half
+                // the bytes); this keeps it on the HBM roofline.
+                float part = 0.0f;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) part = __fadd_rn(__fmul_rn(a[r][u].v[e], pv[u].v[e]), part);
+                }
+                acc[r] = __dadd_rn(acc[r], (double)part);
+            } else {
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+#pragma unroll
+                    for (int e = 0; e < E; ++e) acc[r] = prod_acc(a[r][u].v[e], pv[u].v[e], acc[r]);
+                }
+            }
+        }
+    };
+    const T *pa = arow0 + E * tid;
+    const T *pp = gp + E * tid;
+    const long long nfull = lda / CH;
+    for (long long k = 0; k < nfull; ++k, pa += CH, pp += CH) chunk(pa, pp, kFalse{}, 0);
+    if (nfull * CH < lda) chunk(pa, pp, kTrue{}, nfull * CH + E * tid);
+#pragma unroll
+    for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
+    if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) red[warp][r] = acc[r];
+    }
+    __syncthreads();
+    double contrib = 0.0;
+    if (warp == 0) {
+        if (lane < R) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < NWARP; ++w) sum = __dadd_rn(sum, red[w][lane]);
+            const T stored = (T)sum;
+            Ap_rs[lane] = stored;
+            contrib = __dmul_rn((double)p_rs[lane], (double)stored);
+        }
+        contrib = warp_sum(contrib);
+    }
+    __syncthreads();
+    return contrib;
+}
+
+template <typename T, int R, int U = 4, int NT = 256, int CPS = 2, int VB = 16>
+__global__ void __launch_bounds__(NT, CPS) lamcg_rowsweep_kernel(GemvArgs g)
+{
+    static_assert(R == 8, "the tail decomposition below is written for 8-row passes");
+    __shared__ double red[NT / 32][kCtaRowMaxR];
     const T *gA = static_cast<const T *>(g.A), *gp = static_cast<const T *>(g.p);
     T *gAp = static_cast<T *>(g.Ap);
     if (g.check_done && ld_volatile_int(&g.st->done)) return;
-    const unsigned long long seq = gemv_peer_prologue(g);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long seq;
+    if (!gemv_peer_prologue(g, seq)) return; // peer flag timeout: error recorded, loop latched done
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = gridDim.x, bid = blockIdx.x;
     const long long base = g.rows / G, rem = g.rows % G;
     const long long r0 = bid * base + (bid < rem ? bid : rem);
     const long long rcnt = base + (bid < rem ? 1 : 0);
     const uint64_t polA = l2_policy_evict_first();
+    const T *prow = gp + g.row_offset; // p is indexed globally
     double cta_dot = 0.0;
-    const long long ngroups = (g.rows + R - 1) / R;
-    const long long npass = RRB ? (ngroups - bid + G - 1) / G : (rcnt + R - 1) / R;
-    for (long long k = 0; k < npass; ++k) {
-        const long long rs = RRB ? (bid + k * G) * R : r0 + k * R;       // first row of this pass
-        const long long left = (RRB ? g.rows : r0 + rcnt) - rs;
-        const int nr = left < R ? (int)left : R;
-        const T *arow0 = gA + rs * g.lda;
-        double acc[R];
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = 0.0;
-        for (long long c0 = 0; c0 < g.lda; c0 += CH) {
-            Vec16<T> pv[U];
-            bool cv[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                const long long c = c0 + E * tid + (long long)u * NT * E;
-                cv[u] = c < g.lda;
-                if (cv[u]) pv[u] = ldg_vec16(gp + c);
-                else {
-#pragma unroll
-                    for (int e = 0; e < E; ++e) pv[u].v[e] = T(0);
-                }
-            }
-            Vec16<T> a[R][U];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-#pragma unroll
-                for (int u = 0; u < U; ++u) {
-                    const long long c = c0 + E * tid + (long long)u * NT * E;
-                    if (cv[u] && r < nr) {
-                        if constexpr (PF && sizeof(T) == 8) {
-                            const double2 t2 = ldg_stream_f64x2_pf256(reinterpret_cast<const double *>(arow0 + (long long)r * g.lda + c), polA);
-                            a[r][u].v[0] = t2.x;
-                            a[r][u].v[1] = t2.y;
-                        } else {
-                            a[r][u] = ldg_stream16(arow0 + (long long)r * g.lda + c, polA);
-                        }
-                    } else {
-#pragma unroll
-                        for (int e = 0; e < E; ++e) a[r][u].v[e] = T(0);
-                    }
-                }
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if constexpr (sizeof(T) == 4) {
-                    // fp32 storage: the U*E (= 16) products of this thread's slice of the chunk are summed in fp32
-                    // (unfused, like the reference's float loop, but only 16 terms deep), then folded into the fp64
-                    // accumulator once per chunk: converting every product to fp64 made the kernel FP64-pipe bound
-                    // (same 10.9 ms as the fp64 GEMV for half the bytes); this keeps it on the HBM roofline.
-                    float part = 0.0f;
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-#pragma unroll
-                        for (int e = 0; e < E; ++e) part = __fadd_rn(__fmul_rn(a[r][u].v[e], pv[u].v[e]), part);
-                    }
-                    acc[r] = __dadd_rn(acc[r], (double)part);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < U; ++u) {
-#pragma unroll
-                        for (int e = 0; e < E; ++e) acc[r] = prod_acc(a[r][u].v[e], pv[u].v[e], acc[r]);
-                    }
-                }
-            }
-        }
-#pragma unroll
-        for (int r = 0; r < R; ++r) acc[r] = warp_sum(acc[r]);
-        if (lane == 0) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) red[warp][r] = acc[r];
-        }
-        __syncthreads();
-        if (warp == 0) {
-            double contrib = 0.0;
-            if (lane < nr) {
-                double sum = 0.0;
-#pragma unroll
-                for (int w = 0; w < NWARP; ++w) sum = __dadd_rn(sum, red[w][lane]);
-                const T stored = (T)sum;
-                gAp[rs + lane] = stored;
-                contrib = __dmul_rn((double)gp[g.row_offset + rs + lane], (double)stored);
-            }
-            contrib = warp_sum(contrib);
-            cta_dot = __dadd_rn(cta_dot, contrib);
-        }
-        __syncthreads();
+    long long rs = r0;
+    const long long rend = r0 + rcnt;
+    for (; rs + R <= rend; rs += R)
+        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, R, U, NT, VB>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
+    // tail: < 8 rows left, same number of loads in flight per pass
+    if (rs + 4 <= rend) {
+        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 4, 2 * U, NT, VB>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
+        rs += 4;
     }
+    if (rs + 2 <= rend) {
+        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 2, 4 * U, NT, VB>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
+        rs += 2;
+    }
+    if (rs < rend) cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 1, 4 * U, NT, VB>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
     if (warp == 0) grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane, &g.pv, 0, g.par, seq);
 }
 
@@ -489,7 +521,7 @@ __global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
     if (v.pv.nranks > 1) { // peer mode: the all-reduce of p.Ap is a wait on nranks flags + a fixed-order sum
         seq = st->seq_base + (unsigned long long)st->iter[v.par] + 1ull;
         PeerHeader *me = peer_hdr(v.pv, v.pv.me);
-        peer_wait_all(me->pap_flag, v.pv.nranks, seq, &st->error);
+        if (!peer_wait_all(me->pap_flag, v.pv.nranks, seq, st, v.pv.timeout_cycles)) return;
         if (threadIdx.x == 0) s_pAp = peer_sum_slots(me->pap_slot[v.par], v.pv.nranks);
         __syncthreads();
         pAp = s_pAp;
@@ -570,7 +602,7 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
     if (v.pv.nranks > 1) {
         const unsigned long long seq = st->seq_base + (unsigned long long)it0 + 1ull;
         PeerHeader *me = peer_hdr(v.pv, v.pv.me);
-        peer_wait_all(me->rrn_flag, v.pv.nranks, seq, &st->error);
+        if (!peer_wait_all(me->rrn_flag, v.pv.nranks, seq, st, v.pv.timeout_cycles)) return;
         if (threadIdx.x == 0) s_rrn = peer_sum_slots(me->rrn_slot[v.par], v.pv.nranks);
         __syncthreads();
         rr_new = s_rrn;
@@ -654,7 +686,7 @@ __global__ void __launch_bounds__(256) peer_gather_put_kernel(PeerView pv, const
 
 __global__ void __launch_bounds__(32) peer_gather_wait_kernel(PeerView pv, unsigned long long gseq, DevState *st)
 {
-    peer_wait_all(peer_hdr(pv, pv.me)->gather_flag, pv.nranks, gseq, &st->error);
+    peer_wait_all(peer_hdr(pv, pv.me)->gather_flag, pv.nranks, gseq, st, pv.timeout_cycles);
 }
 
 // =============================================================================================

@@ -35,17 +35,25 @@ int main(int argc, char **argv)
             if (std::fread(hdr, sizeof hdr, 1, f) == 1) n_hint = (size_t)hdr[0];
             std::fclose(f);
         }
-        if (!cg.ok()) rc = 1;
-        if (rc == 0) cg.init_comm(world, n_hint);
-        if (rc == 0 && !cg.load_matrix_from_file(matrix)) {
+        // every outcome is agreed over the ranks (all_ok) so that they leave together
+        if (!world.all_ok(cg.ok())) rc = 1;
+        if (rc == 0) {
+            cg.init_comm(world, n_hint);
+            if (!world.all_ok(cg.ok())) {
+                if (root) std::fprintf(stderr, "Failed to initialise the multi-GPU exchange\n");
+                rc = 1;
+            }
+        }
+        if (rc == 0 && !world.all_ok(cg.load_matrix_from_file(matrix))) {
             if (root) std::fprintf(stderr, "Failed to read matrix\n");
             rc = 1;
         }
-        if (rc == 0 && !cg.load_rhs_from_file(rhs)) {
+        if (rc == 0 && !world.all_ok(cg.load_rhs_from_file(rhs))) {
             if (root) std::fprintf(stderr, "Failed to read right hand side\n");
             rc = 2;
         }
         if (rc == 0) {
+            world.barrier(); // ranks may finish the file ingest far apart: meet before the first in-kernel flag wait
             const auto t0 = std::chrono::steady_clock::now();
             cg.solve(max_iters, rel_error);
             if (root) std::printf("Time elapsed using the B200 solver:%g s\n", std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count());

@@ -34,16 +34,46 @@ def test_library_exports_every_declared_symbol(lamcg):
     assert sorted(lamcg._SIGNATURES) == header_symbols()
 
 
+def _sass():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("sass_summary", os.path.join(REPO, "tools", "sass_summary.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
 def test_library_is_sm100a_native_code(lamcg):
-    """The shipped cubin is sm_100a and the GEMV really contains TMA bulk copies (UBLKCP) and
-    mbarrier waits (SYNCS) — cuobjdump works without a GPU."""
+    """The shipped cubin is sm_100a, and the instruction mix of the K1 kernels is what DESIGN.md says it is (cuobjdump works
+    without a GPU): the DEFAULT row sweep streams A with 128-bit non-allocating loads (LDG.E.NA.128), 8 rows x 4 loads per
+    thread in its main loop, unfused DMUL + DADD (no DFMA: the reference's x86-64 build does not contract), no spills; the
+    256-bit shape really uses the sm_100 256-bit load; the TMA shapes contain bulk copies (UBLKCP) and mbarrier waits (SYNCS)."""
     if not os.path.exists(lamcg.LIB_PATH):
         lamcg.build()
     out = subprocess.run(["cuobjdump", "-lelf", lamcg.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN6lamcgk15gemv_tma_kernelILi16ELi256ELi6EEEvNS_8GemvArgsE",
-                           lamcg.LIB_PATH], capture_output=True, text=True).stdout
-    assert "UBLKCP" in sass and "SYNCS" in sass
+    S = _sass()
+    ks = S.kernels(lamcg.LIB_PATH)
+
+    def one(fragment):
+        names = [k for k in ks if fragment in k]
+        assert len(names) == 1, (fragment, names)
+        return ks[names[0]]
+
+    for frag in ("rowsweep_kernelIdLi8ELi4ELi512ELi1ELi16E", "rowsweep_kernelIdLi8ELi4ELi256ELi2ELi16E"):  # variants 36 / 32 (defaults)
+        k = one(frag)
+        loop = S.mix(S.main_loop(k))
+        assert loop["LDG.E.NA.128.CONSTANT"] == 32 and loop["LDG.E.128.CONSTANT"] == 4, loop   # A: 8 rows x 4; p: 4
+        assert loop["DMUL"] == 64 and loop["DADD"] == 64 and loop.get("DFMA", 0) == 0, loop
+        assert len(S.main_loop(k)) <= 220                                                   # loads + flops + ~30: no address recomputation
+        whole = S.mix(k)
+        assert not any(op.startswith(("STL", "LDL")) for op in whole), "register spills in the default K1"
+        assert not any("UBLKCP" in op for op in whole)
+    for frag in ("rowsweep_kernelIdLi8ELi2ELi512ELi1ELi32E", "rowsweep_kernelIdLi8ELi2ELi256ELi2ELi32E"):  # variants 46 / 42
+        loop = S.mix(S.main_loop(one(frag)))
+        assert loop["LDG.E.NA.ENL2.256.CONSTANT"] == 16, loop
+    for frag in ("lamcg_tmaring_kernel", "lamcg_warprows_tmap_kernel"):
+        whole = S.mix(one(frag))
+        assert any(op.startswith("UBLKCP") for op in whole) and any(op.startswith("SYNCS") for op in whole), frag
 
 
 def test_no_cpu_fallback(lamcg):

@@ -15,7 +15,8 @@ from oracle import fileformat, random_spd
 pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 TEST_DIR = os.path.join(REPO, "2024-eumaster4hpc-student-challenge_b200", "test")
-GETOPT = os.path.join(TEST_DIR, "test_CG_MultiGPUS_CUDA_NCCL.out")
+GETOPT = os.path.join(TEST_DIR, "test_CG_MultiGPUS_CUDA_MPI.out")        # 9-field CSV line (test_CG_CPU_MPI_OMP.cpp:201-203)
+GETOPT_NCCL = os.path.join(TEST_DIR, "test_CG_MultiGPUS_CUDA_NCCL.out") # 10 fields: + communicator init after io_s (NCCL.cu:329-334)
 POSITIONAL = os.path.join(TEST_DIR, "test_CG_single_GPU.out")
 
 
@@ -40,6 +41,38 @@ def test_generate_mode_csv_line_matches_reference_rows(golden, tmp_path):
         x = fileformat.read_vector(str(tmp_path / "sol.bin"))
         o = oracle.cg_solve_generated(g["n"], g["max_iters"], 1e-9)
         assert np.linalg.norm(x - o.x) / np.linalg.norm(o.x) <= 1e-12  # we save x (the reference saves b: defect 2)
+
+
+@pytest.mark.parametrize("exe,fields", [(GETOPT, 9), (GETOPT_NCCL, 10)])
+def test_csv_field_count_per_executable(exe, fields, tmp_path):
+    """The reference ships two getopt GPU executables whose CSV lines differ by one field: test_CG_MultiGPUS_CUDA_MPI.out prints
+    n,ranks,threads,io_s,avg_gemv_s,avg_iter_s,iters,rel_err,total_s and test_CG_MultiGPUS_CUDA_NCCL.out inserts the communicator
+    init seconds after io_s (ConjugateGradient_MultiGPUS_CUDA_NCCL.cu:329-334, e.g. TESTS/BEST_RESULTS:420
+    `10000,1,1,0.986,1.54201,0.000698578,0.000810044,323,9.424e-10,1.832`).  Same here, in generate and in file mode."""
+    n, k = 2048, 15
+    o = oracle.cg_solve_generated(n, k, 1e-9)
+    res = run([exe, "-s", str(n), "-i", str(k), "-e", "1e-9", "-o", str(tmp_path / "sol.bin")])
+    assert res.returncode == 0, res.stderr
+    assert res.stdout.endswith("\n") and res.stdout.count("\n") == 1      # exactly one line, closed by std::endl
+    f = res.stdout.strip().split(",")
+    assert len(f) == fields, res.stdout
+    shift = fields - 9
+    assert [int(f[0]), int(f[1]), int(f[2])] == [n, 1, 1]
+    assert all(float(v) >= 0.0 for v in f[3:6 + shift])                   # io_s [, comm_init_s], avg_gemv_s, avg_iter_s
+    assert int(f[6 + shift]) == o.iters == k + 1
+    assert math.isclose(float(f[7 + shift]), o.rel, rel_tol=2e-5)
+    assert f[8 + shift] == str(int(float(f[8 + shift])))                   # whole seconds in generate mode
+    A, b = random_spd.random_spd_system(64, 5)
+    pa, pb = str(tmp_path / "A.bin"), str(tmp_path / "b.bin")
+    fileformat.write_matrix(pa, A)
+    fileformat.write_matrix(pb, b)
+    res = run([exe, "-A", pa, "-b", pb, "-o", str(tmp_path / "x.bin"), "-i", "1000", "-e", "1e-9"])
+    assert res.returncode == 0, res.stderr
+    f = res.stdout.strip().split(",")
+    assert len(f) == fields and int(f[0]) == 64, res.stdout
+    # verbose mode suppresses the driver-side fields but the class-side ones (n, and avg_gemv..rel) still appear (MPI_OMP.hpp:203-205,122-127)
+    res = run([exe, "-s", "64", "-v", "-o", str(tmp_path / "v.bin")])
+    assert res.returncode == 0 and "Number of threads: 1" in res.stdout
 
 
 def test_file_mode_both_drivers_and_reference_cli_interop(tmp_path):

@@ -29,7 +29,7 @@ def solver32(lamcg):
     s.close()
 
 
-@pytest.mark.parametrize("variant", [0, 30, 31, 32, 34, 36, 37, 38, 69])
+@pytest.mark.parametrize("variant", [0, 32, 36, 42, 46])
 @pytest.mark.parametrize("n", [1, 2, 3, 5, 16, 33, 255, 257, 1000, 1025, 4099])
 def test_gemv_f32_integer_inputs_bit_exact(solver32, variant, n):
     rng = np.random.default_rng(7 * n + variant)
@@ -46,7 +46,7 @@ def test_gemv_f32_integer_inputs_bit_exact(solver32, variant, n):
 def test_f32_variant_restrictions(solver32, lamcg):
     solver32.generate_matrix(64, 64)
     with pytest.raises(lamcg.LamcgError):
-        solver32.set_option("gemv_variant", 14)      # the ldg / TMA families are fp64 only
+        solver32.set_option("gemv_variant", 11)      # the ldg / TMA families are fp64 only
     solver32.set_option("gemv_variant", 0)
     solver32.generate_rhs()
     solver32.set_option("loop_mode", 3)              # so is the persistent loop

@@ -41,8 +41,9 @@ def test_ranked_solve_matches_oracle(comm, world, tmp_path):
         json.dump(rep, f, indent=1)
 
 
+@pytest.mark.parametrize("exe_name,fields", [("test_CG_MultiGPUS_CUDA_MPI.out", 9), ("test_CG_MultiGPUS_CUDA_NCCL.out", 10)])
 @pytest.mark.parametrize("comm", ["nccl", "peer"])
-def test_cpp_driver_forked_ranks(comm, tmp_path):
+def test_cpp_driver_forked_ranks(comm, exe_name, fields, tmp_path):
     """The getopt driver with LAMCG_NGPUS=2: RankWorld forks one process per GPU (the reference uses
     srun -n 2), rank 0 prints the CSV line and writes the gathered x."""
     if _ngpus() < 2:
@@ -51,16 +52,17 @@ def test_cpp_driver_forked_ranks(comm, tmp_path):
     import numpy as np
     import oracle
     from oracle import fileformat
-    exe = os.path.join(REPO, "2024-eumaster4hpc-student-challenge_b200", "test", "test_CG_MultiGPUS_CUDA_NCCL.out")
+    exe = os.path.join(REPO, "2024-eumaster4hpc-student-challenge_b200", "test", exe_name)
     sol = str(tmp_path / "sol.bin")
     env = dict(os.environ, LAMCG_NGPUS="2", LAMCG_COMM=comm)
     n, it = 10007, 150
     res = subprocess.run([exe, "-s", str(n), "-i", str(it), "-e", "1e-9", "-o", sol], capture_output=True, text=True, env=env, timeout=200)
     assert res.returncode == 0, res.stdout + res.stderr
     f = res.stdout.strip().split(",")
-    assert len(f) == 9 and int(f[0]) == n and int(f[1]) == 2 and int(f[6]) == it + 1
+    shift = fields - 9  # the NCCL-named executable prints the communicator-init seconds after io_s
+    assert len(f) == fields and int(f[0]) == n and int(f[1]) == 2 and int(f[6 + shift]) == it + 1
     o = oracle.cg_solve_generated(n, it, 1e-9)
-    assert math.isclose(float(f[7]), o.rel, rel_tol=2e-5)
+    assert math.isclose(float(f[7 + shift]), o.rel, rel_tol=2e-5)
     x = fileformat.read_vector(sol)
     assert np.linalg.norm(x - o.x) / np.linalg.norm(o.x) <= 1e-12
 

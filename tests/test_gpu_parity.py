@@ -71,11 +71,15 @@ def solver(lamcg):
 
 
 # ------------------------------------------------------------------------------------- K1: GEMV
-VARIANTS = [1, 11, 12, 13, 14, 15, 16, 17, 18, 2, 21, 22, 23, 24, 25, 26, 27, 28, 29, 30, 31, 32, 33, 34, 35, 36, 37, 38, 39, 41, 44, 51, 52, 61, 62, 63, 65, 67, 68, 69, 70, 71, 72, 73, 74]
+# the six K1 shapes the library keeps (lamcg.cu: make_plan): row sweep 128-bit (32, 36 = defaults) and 256-bit (42, 46) loads,
+# warp-per-rows with TMA-staged p (11), TMA ring (2)
+VARIANTS = [32, 36, 42, 46, 11, 2]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
-@pytest.mark.parametrize("n", [1, 2, 3, 7, 16, 33, 255, 256, 257, 1000, 1025, 2048, 4099])
+# 1..9 and 15..17: every tail decomposition (4 + 2 + 1 rows) of the row sweep in a single CTA; 1000 / 1184 / 1185 / 4099: 6-8 and 27-28
+# rows per CTA on 148 SMs (full passes + every tail); 255..257, 1025, 2048: chunk and padding edges
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 6, 7, 8, 9, 15, 16, 17, 33, 255, 256, 257, 1000, 1025, 1184, 1185, 2048, 4099])
 def test_gemv_integer_inputs_bit_exact(solver, variant, n):
     """Integer-valued A and p: every partial sum is exact, so any summation order must reproduce the
     oracle's sequential sum bit for bit.  Catches indexing, padding and tail bugs at ragged sizes."""
@@ -90,7 +94,7 @@ def test_gemv_integer_inputs_bit_exact(solver, variant, n):
     assert d == oracle.dot(p, y_ref)
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", VARIANTS)
 @pytest.mark.parametrize("n", [257, 1500, 4096])
 def test_gemv_random_inputs(solver, variant, n):
     rng = np.random.default_rng(n)
@@ -105,7 +109,7 @@ def test_gemv_random_inputs(solver, variant, n):
     assert abs(d - oracle.dot(p, y_ref)) <= 1e-12 * float(np.abs(p) @ np.abs(y_ref))
 
 
-@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("variant", VARIANTS)
 def test_gemv_generated_matrix_matches_generator(solver, variant):
     """Device generator (MPI_OMP.hpp:237-247) + GEMV on an integer vector == oracle, bit exact."""
     n = 3001
@@ -440,24 +444,49 @@ def test_non_finite_systems_report_like_the_reference(solver, loop_mode):
     assert r.converged and r.numerical_breakdown == 0 and r.iterations == 32
 
 
-def test_refused_cooperative_launch_falls_back_to_the_graph_loop(solver, lamcg, monkeypatch):
+def test_refused_cooperative_launch_falls_back_to_the_graph_loop(solver, lamcg):
     """The one-kernel loop needs all its CTAs resident at once.  When the device refuses the cooperative launch (simulated by the
-    LAMCG_PERSIST_FAIL test hook) a solve whose loop was chosen by size runs through the graph loop with the same result; a
-    solve that asked for loop_mode 3 explicitly reports the failure."""
+    debug_persist_fail option, a test hook) a solve whose loop was chosen by size runs through the graph loop with the same
+    result and leaves no error message behind; a solve that asked for loop_mode 3 explicitly reports the failure."""
     n = 1000
     solver.generate_matrix(n, n)
     solver.generate_rhs()
     o = oracle.cg_solve_generated(n, 10000, 1e-9)
     r = solver.solve(10000, 1e-9)
     assert r.kernel_launches == 1 and r.iterations == o.iters            # auto: the one-kernel loop
-    monkeypatch.setenv("LAMCG_PERSIST_FAIL", "1")
+    solver.set_option("debug_persist_fail", 1)
     r = solver.solve(10000, 1e-9)
     assert r.kernel_launches > 1 and r.converged and r.iterations == o.iters
     assert rel_l2(solver.solution(), o.x) <= X_TOL
+    assert (lamcg.lib().lamcg_last_error(solver._h) or b"") == b""      # the fallback succeeded: no stale error text
     solver.set_option("loop_mode", 3)
     with pytest.raises(lamcg.LamcgError) as e:
         solver.solve(10000, 1e-9)
     assert e.value.code == -2 and "cooperative launch" in e.value.message
-    monkeypatch.delenv("LAMCG_PERSIST_FAIL")
+    solver.set_option("debug_persist_fail", 0)
     r = solver.solve(10000, 1e-9)
     assert r.kernel_launches == 1 and r.iterations == o.iters
+
+
+@pytest.mark.parametrize("persist_variant", [0, 1, 3])
+def test_one_kernel_loop_on_a_device_with_few_sms(solver, lamcg, persist_variant):
+    """Every generation of the one-kernel loop owns one row per thread (512 per CTA).  On a device that offers few SMs (MIG slice,
+    MPS limit; simulated with persist_grid) n near 16384 needs more: the size-chosen loop must fall back to the graph loop and
+    still be right, an explicit loop_mode 3 must be refused — never a silent wrong x (round-1 ADVICE)."""
+    n = 9000
+    solver.generate_matrix(n, n)
+    solver.generate_rhs()
+    o = oracle.cg_solve_generated(n, 60, 1e-9)
+    solver.set_option("persist_variant", persist_variant)
+    solver.set_option("persist_grid", 16)                                # ceil(9000 / 16) = 563 rows per CTA > 512
+    r = solver.solve(60, 1e-9)
+    assert r.kernel_launches > 1 and r.iterations == o.iters
+    assert rel_l2(solver.solution(), o.x) <= X_TOL_GEN
+    solver.set_option("loop_mode", 3)
+    with pytest.raises(lamcg.LamcgError) as e:
+        solver.solve(60, 1e-9)
+    assert e.value.code == -1 and "rows per CTA" in e.value.message
+    solver.set_option("persist_grid", 18)                                # 500 rows per CTA: fits, and must be right on 18 CTAs
+    r = solver.solve(60, 1e-9)
+    assert r.kernel_launches == 1 and r.iterations == o.iters
+    assert rel_l2(solver.solution(), o.x) <= X_TOL_GEN

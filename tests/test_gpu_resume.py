@@ -15,7 +15,7 @@ from oracle import fileformat, random_spd
 
 pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GETOPT = os.path.join(REPO, "2024-eumaster4hpc-student-challenge_b200", "test", "test_CG_MultiGPUS_CUDA_NCCL.out")
+GETOPT = os.path.join(REPO, "2024-eumaster4hpc-student-challenge_b200", "test", "test_CG_MultiGPUS_CUDA_MPI.out")
 
 
 def _generated(lamcg, n, loop_mode, dtype="f64"):

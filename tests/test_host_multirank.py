@@ -103,3 +103,19 @@ def test_single_rank_bootstrap_is_a_noop():
     assert lamcg_b200.launch.bootstrap_comm(s) == "none" and s.got_id is None
     assert lamcg_b200.launch.broadcast_bytes(b"x") == b"x"
     assert lamcg_b200.launch.allgather_bytes(b"y") == [b"y"]
+
+
+def test_set_matrix_shape_validation_happens_before_the_c_call(lamcg):
+    """Solver.set_matrix: layout 0 takes the whole (n, n) matrix, layout 1 this rank's (local_rows, n) block; a short or
+    non-square array must raise ValueError in Python instead of letting the library's 2-D copy read past the buffer."""
+    import types
+    check = lamcg.Solver._check_matrix_shape
+    single = types.SimpleNamespace(rank=0, nranks=1)
+    last_of_3 = types.SimpleNamespace(rank=2, nranks=3)
+    assert check(single, (7, 7), 0) == 7
+    assert check(last_of_3, (10, 10), 0) == 10
+    assert check(last_of_3, (4, 10), 1) == 10          # 10 // 3 = 3 rows + the remainder row on the last rank
+    for who, shape, layout in [(single, (6, 7), 0), (single, (7,), 0), (single, (7, 7, 1), 0), (last_of_3, (3, 10), 1),
+                               (last_of_3, (10, 10), 1), (single, (0, 0), 0), (single, (7, 7), 2)]:
+        with pytest.raises(ValueError):
+            check(who, shape, layout)

@@ -11,7 +11,7 @@ import lamcg_b200  # noqa: E402
 
 ap = argparse.ArgumentParser()
 ap.add_argument("n", nargs="*", type=int, default=[100000])
-ap.add_argument("--variants", default="1,11,12,13,14,2,21,22,23,24,25,26,27")
+ap.add_argument("--variants", default="36,46,32,42,11,2")
 ap.add_argument("--ranks", type=int, default=1, help="emulate the row block of rank 0 of this many ranks")
 ap.add_argument("--reps", type=int, default=10)
 ap.add_argument("--out", default=None)

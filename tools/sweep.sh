@@ -8,7 +8,7 @@ OUT=${1:-sweep_results.txt}
 MODE=${2:-gen}
 DIR=${3:-io}
 HERE="$(cd "$(dirname "$0")/.." && pwd)"
-EXE="$HERE/2024-eumaster4hpc-student-challenge_b200/test/test_CG_MultiGPUS_CUDA_NCCL.out"
+EXE=${EXE:-"$HERE/2024-eumaster4hpc-student-challenge_b200/test/test_CG_MultiGPUS_CUDA_MPI.out"}  # 9 fields; ..._NCCL.out adds comm_init_s after io_s (10)
 GPUS=${GPUS:-1}
 ITERS=${ITERS:-15}
 SIZES=${SIZES:-"10000 20000 30000 40000 50000"}
