@@ -54,7 +54,8 @@ class lamcg_info(ctypes.Structure):
                 ("lda", ctypes.c_size_t), ("rank", ctypes.c_int), ("nranks", ctypes.c_int), ("device", ctypes.c_int),
                 ("sm_count", ctypes.c_int), ("comm_mode", ctypes.c_int), ("has_matrix", ctypes.c_int),
                 ("has_rhs", ctypes.c_int), ("gemv_variant", ctypes.c_int), ("gemv_grid", ctypes.c_int),
-                ("gemv_block", ctypes.c_int), ("gemv_smem_bytes", ctypes.c_int), ("dtype", ctypes.c_int)]
+                ("gemv_block", ctypes.c_int), ("gemv_smem_bytes", ctypes.c_int), ("dtype", ctypes.c_int),
+                ("ingest_threads", ctypes.c_int), ("ingest_chunks", ctypes.c_int)]
 
 
 def build(verbose: bool = False) -> str:

@@ -77,14 +77,20 @@ struct lamcg {
     // options
     long long opt_gemv_variant = 0, opt_loop_mode = 0, opt_chunk_iters = 16, opt_time_gemv = 0, opt_history = 1;
     long long opt_gemv_ctas_per_sm = 0;
-    long long opt_ingest_threads = 4;
-    long long opt_ingest_chunk_bytes = 32ll << 20; // staging buffer size of the file ingest (tests shrink it to force many chunks)
+    long long opt_ingest_threads = 8;
+    long long opt_ingest_chunk_bytes = 4ll << 20; // staging buffer size of the file ingest (tests shrink it to force many chunks)
     long long opt_peer_timeout_s = 600;   // bound of every peer flag wait; ranks may finish a cold-cache ingest minutes apart
     long long opt_persist_grid = 0;       // 0: one CTA per SM; k > 0: at most k CTAs in the one-kernel loop (tests: small-device behaviour)
     long long opt_debug_persist_fail = 0; // test hook: pretend the cooperative launch was refused
+    long long opt_spd_simt = 0;           // 1: the SPD generator's products on the SIMT kernel only (comparison / fallback)
     int clock_khz = 1965000;
+    char *ingest_pool = nullptr;          // pinned staging buffers of the file ingest (kept between loads)
+    size_t ingest_pool_bytes = 0;
+    int last_ingest_threads = 0;
+    long long last_ingest_chunks = 0;
     long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
-    long long opt_persist_variant = 0;    // 0 auto (second generation for n <= 2048, first below 4096, third from there) | 1 first | 2 second (n <= 4096) | 3 third
+    long long opt_persist_variant = 0;    // 0 auto (fourth generation for n <= 2048, first below 4096, third from there) | 1 first | 2 second (n <= 4096) | 3 third | 4 fourth (n <= 4096)
+    long long opt_persist_poll = 0;       // generation 4: polling load of the gathered Ap: 0 ld.relaxed.gpu.v4.u64 | 1 ld.relaxed.gpu.v2.u64 x2 | 2 ld.cg.v2.u64 x2
 
     // comm
     int comm_mode = kCommNone;
@@ -96,7 +102,7 @@ struct lamcg {
     unsigned long long seq_next = 1, gather_seq = 0;
     double *gemm_ws = nullptr; // split-K workspace of the SPD generator (alive only inside lamcg_random_spd_system)
     unsigned long long *persist_ll = nullptr; // [2][G][G][2] tagged partial words (per-CTA inboxes)
-    int persist_ll_grid = 0;
+    size_t persist_ll_words = 0;
 
     // graph cache
     cudaGraphExec_t graph_exec = nullptr;
@@ -450,12 +456,13 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
 
     int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
     if (h->opt_persist_grid > 0) grid = (int)std::min<long long>(grid, h->opt_persist_grid);
-    const size_t ll_words = (size_t)2 * kLLStride * grid * grid;
-    if (!h->persist_ll || h->persist_ll_grid < grid) {
+    // generations 1-3: [2][G][G][kLLStride] tagged scalar words; generation 4: [2][lda][2] tagged entries of the gathered Ap
+    const size_t ll_words = std::max((size_t)2 * kLLStride * grid * grid, (size_t)4 * h->lda);
+    if (!h->persist_ll || h->persist_ll_words < ll_words) {
         cudaFree(h->persist_ll);
         h->persist_ll = nullptr;
         CK(cudaMalloc(&h->persist_ll, ll_words * sizeof(unsigned long long)));
-        h->persist_ll_grid = grid;
+        h->persist_ll_words = ll_words;
     }
     const int rows_max = (int)((h->n + grid - 1) / grid);
     // every generation of the kernel handles one owned row per thread (x, r, Ap of row r0 + tid): a device that offers few SMs
@@ -469,17 +476,28 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     // persist_variant: 0 auto | 1 first generation (row tasks) | 2 second (p in registers, all rows in shared memory; n <= 4096;
     // auto for n <= 2048) | 3 third (K1's streaming row sweep inside the loop; auto above)
     const bool v2_ok = h->lda <= 4096;
-    const bool v2 = v2_ok && (h->opt_persist_variant == 2 || (h->opt_persist_variant == 0 && h->lda <= 2048));
+    const bool v4 = v2_ok && (h->opt_persist_variant == 4 || (h->opt_persist_variant == 0 && h->lda <= 2048));
+    const bool v2 = v2_ok && h->opt_persist_variant == 2;
     // auto above lda = 2048: up to lda < 4096 the first generation still keeps a useful share of the rows in shared memory
     // (n = 3000: 87.7 k it/s vs 72.9 k for the streaming sweep; equal at 4096), beyond that the sweep wins (n = 8192: 12.2 k vs 9.9 k)
-    const bool v3 = !v2 && (h->opt_persist_variant == 3 || (h->opt_persist_variant == 0 && h->lda >= 4096));
-    if (h->opt_persist_variant == 2 && !v2) return h->fail(LAMCG_ERR_INVALID, "persist_variant 2 needs n <= 4096");
-    if (h->opt_persist_variant < 0 || h->opt_persist_variant > 3) return h->fail(LAMCG_ERR_INVALID, "persist_variant must be 0..3");
+    const bool v3 = !v2 && !v4 && (h->opt_persist_variant == 3 || (h->opt_persist_variant == 0 && h->lda >= 4096));
+    if ((h->opt_persist_variant == 2 || h->opt_persist_variant == 4) && !v2_ok) return h->fail(LAMCG_ERR_INVALID, "persist_variant 2 and 4 need n <= 4096");
+    if (h->opt_persist_variant < 0 || h->opt_persist_variant > 4) return h->fail(LAMCG_ERR_INVALID, "persist_variant must be 0..4");
+    if (h->opt_persist_poll < 0 || h->opt_persist_poll > 2) return h->fail(LAMCG_ERR_INVALID, "persist_poll must be 0..2");
     const void *kernel = (const void *)cg_persistent_kernel;
     int segs = 1;
     size_t fixed;
     bool resident_rows = true;
-    if (v2) {
+    if (v4) {
+        const int pl = h->lda <= 1024 ? 0 : h->lda <= 2048 ? 1 : 2;
+        static const void *const table[3][3] = {
+            {(const void *)cg_persistent_v4_kernel<2, 0>, (const void *)cg_persistent_v4_kernel<2, 1>, (const void *)cg_persistent_v4_kernel<2, 2>},
+            {(const void *)cg_persistent_v4_kernel<4, 0>, (const void *)cg_persistent_v4_kernel<4, 1>, (const void *)cg_persistent_v4_kernel<4, 2>},
+            {(const void *)cg_persistent_v4_kernel<8, 0>, (const void *)cg_persistent_v4_kernel<8, 1>, (const void *)cg_persistent_v4_kernel<8, 2>}};
+        kernel = table[pl][h->opt_persist_poll];
+        const size_t rows_pad = ((size_t)rows_max + 7) & ~(size_t)7;
+        fixed = rows_pad * (kPersistThreads / 32) * sizeof(double); // per-warp row partials
+    } else if (v2) {
         kernel = h->lda <= 1024 ? (const void *)cg_persistent_v2_kernel<2> : h->lda <= 2048 ? (const void *)cg_persistent_v2_kernel<4>
                                                                                            : (const void *)cg_persistent_v2_kernel<8>;
         const size_t rows_pad = ((size_t)rows_max + 7) & ~(size_t)7;
@@ -557,6 +575,25 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
 }
 
 // ---- file helpers ------------------------------------------------------------------------------
+constexpr int kIngestSlots = 3;        // staging buffers per reader thread
+constexpr int kIngestMaxThreads = 32;
+
+int ensure_ingest_pool(lamcg *h, size_t bytes)
+{
+    if (h->ingest_pool && h->ingest_pool_bytes >= bytes) return LAMCG_OK;
+    if (h->ingest_pool) cudaFreeHost(h->ingest_pool);
+    h->ingest_pool = nullptr;
+    h->ingest_pool_bytes = 0;
+    cudaError_t e = cudaMallocHost(&h->ingest_pool, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        h->ingest_pool = nullptr;
+        return h->fail(LAMCG_ERR_NOMEM, "cudaMallocHost of %.1f MB of ingest staging buffers failed: %s", bytes / 1e6, cudaGetErrorString(e));
+    }
+    h->ingest_pool_bytes = bytes;
+    return LAMCG_OK;
+}
+
 int read_header(lamcg *h, int fd, const char *path, size_t *rows, size_t *cols)
 {
     uint64_t hdr[2];
@@ -786,8 +823,9 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_gemv_ctas_per_sm = env_ll("gemv_ctas_per_sm", 0);
     h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
     h->opt_persist_variant = env_ll("persist_variant", 0);
-    h->opt_ingest_threads = env_ll("ingest_threads", 4);
-    h->opt_ingest_chunk_bytes = env_ll("ingest_chunk_bytes", 32ll << 20);
+    h->opt_persist_poll = env_ll("persist_poll", 0);
+    h->opt_ingest_threads = env_ll("ingest_threads", 8);
+    h->opt_ingest_chunk_bytes = env_ll("ingest_chunk_bytes", 4ll << 20);
     h->opt_peer_timeout_s = env_ll("peer_timeout_s", 600);
     h->opt_persist_grid = env_ll("persist_grid", 0);
     *out = h;
@@ -822,6 +860,7 @@ void lamcg_destroy(lamcg_t *h)
     close_peer_handles(h);
     cudaFree(h->peer_base);
     cudaFree(h->persist_ll);
+    if (h->ingest_pool) cudaFreeHost(h->ingest_pool);
     free_system(h);
     for (cudaEvent_t e : h->gemv_events) cudaEventDestroy(e);
     cudaFree(h->hist);
@@ -848,11 +887,13 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "gemv_ctas_per_sm") h->opt_gemv_ctas_per_sm = value;
     else if (k == "persist_rows_smem") h->opt_persist_rows_smem = value;
     else if (k == "persist_variant") h->opt_persist_variant = value;
+    else if (k == "persist_poll") h->opt_persist_poll = value;
     else if (k == "ingest_threads") h->opt_ingest_threads = value;
     else if (k == "ingest_chunk_bytes") h->opt_ingest_chunk_bytes = value;
     else if (k == "peer_timeout_s") { h->opt_peer_timeout_s = value; h->pv.timeout_cycles = peer_timeout_cycles(h); }
     else if (k == "persist_grid") h->opt_persist_grid = value;
     else if (k == "debug_persist_fail") h->opt_debug_persist_fail = value;
+    else if (k == "spd_simt") h->opt_spd_simt = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->alloc_n) {
@@ -881,6 +922,8 @@ int lamcg_get_info(const lamcg_t *h, lamcg_info *out)
     out->gemv_block = h->plan.block;
     out->gemv_smem_bytes = (int)h->plan.smem;
     out->dtype = h->dtype;
+    out->ingest_threads = h->last_ingest_threads;
+    out->ingest_chunks = (int)std::min<long long>(h->last_ingest_chunks, INT_MAX);
     return LAMCG_OK;
 }
 
@@ -1079,20 +1122,27 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
     rc = alloc_system(h, rows);
     if (rc != LAMCG_OK) { close(fd); return rc; }
     const size_t n = h->n;
-    // Chunked, multi-threaded ingest: T reader threads, each with its own stream and two pinned staging
-    // buffers, interleave over row chunks: pread (page cache / disk -> pinned) of chunk k+T overlaps the
-    // async 2-D H2D copy of chunk k.  One thread tops out near 6 GB/s (a single core's memcpy rate out of the
-    // page cache, the same rate the reference's fread reaches into pageable memory); T threads scale that
-    // until PCIe is the limit.
+    // Chunked, multi-threaded ingest: T reader threads pull row chunks off a shared counter; each owns its own stream and
+    // kIngestSlots pinned staging buffers out of a pool that lives in the handle (pinning memory costs ~0.3 s per GB: round 1
+    // allocated 2 x 32 MB per thread on EVERY load, which is why 8 threads lost to 4 on a 3 GB file).  pread (page cache / disk
+    // -> pinned) of one chunk overlaps the async 2-D H2D copies of the thread's previous chunks.  One thread tops out near
+    // 6 GB/s (a single core's copy rate out of the page cache, the rate the reference's fread reaches into pageable memory);
+    // T threads scale that until PCIe is the limit.  All offsets are 64-bit (the reference's MPI-IO count is an int: n = 50000
+    // on one rank reads garbage, TESTS/BEST_RESULTS:114).
     const size_t row_bytes = n * h->esz; // file elements have the handle's type, like the reference's sizeof(FloatingType)
-    size_t chunk_rows = std::max<size_t>(1, (size_t)(32u << 20) / row_bytes);
+    const size_t chunk_bytes = (size_t)std::max<long long>(row_bytes, std::min<long long>(h->opt_ingest_chunk_bytes, 256ll << 20));
+    size_t chunk_rows = std::max<size_t>(1, chunk_bytes / row_bytes);
     chunk_rows = std::min(chunk_rows, std::max<size_t>(h->local_rows, 1));
     const size_t nchunks = (h->local_rows + chunk_rows - 1) / chunk_rows;
-    int T = (int)std::max<long long>(1, std::min<long long>(h->opt_ingest_threads, 16));
+    int T = (int)std::max<long long>(1, std::min<long long>(h->opt_ingest_threads, kIngestMaxThreads));
     T = (int)std::min<size_t>((size_t)T, std::max<size_t>(nchunks, 1));
+    const size_t slot_bytes = chunk_rows * row_bytes;
+    rc = ensure_ingest_pool(h, (size_t)T * kIngestSlots * slot_bytes);
+    if (rc != LAMCG_OK) { close(fd); return rc; }
     if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * h->esz, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     std::atomic<int> status{LAMCG_OK};
+    std::atomic<size_t> next_chunk{0};
     std::string first_error;
     std::mutex err_mu;
     auto worker = [&](int t) {
@@ -1102,34 +1152,37 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
         };
         if (cudaSetDevice(h->device) != cudaSuccess) return failw(LAMCG_ERR_CUDA, "cudaSetDevice failed in ingest thread");
         cudaStream_t st = nullptr;
-        char *stage[2] = {nullptr, nullptr};
-        cudaEvent_t done[2] = {nullptr, nullptr};
+        cudaEvent_t done[kIngestSlots] = {};
         bool ok = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) == cudaSuccess;
-        for (int i = 0; i < 2 && ok; ++i)
-            ok = cudaMallocHost(&stage[i], chunk_rows * row_bytes) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) failw(LAMCG_ERR_NOMEM, "cudaMallocHost of the ingest buffers failed");
+        for (int i = 0; i < kIngestSlots && ok; ++i) ok = cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming) == cudaSuccess;
+        if (!ok) failw(LAMCG_ERR_CUDA, "stream / event creation failed in ingest thread");
+        char *stage0 = h->ingest_pool + (size_t)t * kIngestSlots * slot_bytes;
         int slot = 0;
-        for (size_t c = (size_t)t; ok && c < nchunks && status.load() == LAMCG_OK; c += (size_t)T, slot ^= 1) {
+        while (ok && status.load() == LAMCG_OK) {
+            const size_t c = next_chunk.fetch_add(1);
+            if (c >= nchunks) break;
             const size_t r = c * chunk_rows;
             const size_t nr = std::min(chunk_rows, h->local_rows - r);
-            cudaEventSynchronize(done[slot]);
+            char *stage = stage0 + (size_t)slot * slot_bytes;
+            cudaEventSynchronize(done[slot]); // the H2D copy that last used this slot has drained
             const off_t off = (off_t)16 + (off_t)((h->row_offset + r) * row_bytes);
-            if (pread_full(fd, stage[slot], nr * row_bytes, off) != 0) {
+            if (pread_full(fd, stage, nr * row_bytes, off) != 0) {
                 failw(LAMCG_ERR_IO, std::string(path) + ": short read in rows " + std::to_string(h->row_offset + r) + ".." +
                                         std::to_string(h->row_offset + r + nr));
                 break;
             }
-            cudaError_t e = cudaMemcpy2DAsync(h->A + r * h->lda * h->esz, h->lda * h->esz, stage[slot], row_bytes, row_bytes, nr,
+            cudaError_t e = cudaMemcpy2DAsync(h->A + r * h->lda * h->esz, h->lda * h->esz, stage, row_bytes, row_bytes, nr,
                                               cudaMemcpyHostToDevice, st);
             if (e != cudaSuccess) { failw(LAMCG_ERR_CUDA, std::string("cudaMemcpy2DAsync failed: ") + cudaGetErrorString(e)); break; }
             cudaEventRecord(done[slot], st);
+            slot = (slot + 1) % kIngestSlots;
         }
         if (st) {
             if (cudaStreamSynchronize(st) != cudaSuccess) failw(LAMCG_ERR_CUDA, "matrix upload failed");
             cudaStreamDestroy(st);
         }
-        for (int i = 0; i < 2; ++i) { if (stage[i]) cudaFreeHost(stage[i]); if (done[i]) cudaEventDestroy(done[i]); }
+        for (int i = 0; i < kIngestSlots; ++i)
+            if (done[i]) cudaEventDestroy(done[i]);
     };
     {
         std::vector<std::thread> pool;
@@ -1137,6 +1190,8 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
         worker(0);
         for (auto &th : pool) th.join();
     }
+    h->last_ingest_threads = T;
+    h->last_ingest_chunks = (long long)nchunks;
     close(fd);
     CK(cudaSetDevice(h->device));
     if (status.load() != LAMCG_OK) return h->fail(status.load(), "%s", first_error.c_str());
@@ -1412,9 +1467,17 @@ int launch_gemm(lamcg *h, const double *A, const double *B, double *C, long long
 {
     if (M <= 0 || N <= 0) return LAMCG_OK;
     GemmArgs g{A, B, C, M, N, K, sai, sak, sbk, sbj, sci, scj, alpha, beta, 0, nullptr};
-    dim3 grid((unsigned)((N + 63) / 64), (unsigned)((M + 63) / 64));
-    // skinny products (the Q1^T Q2 of the lower Gram-Schmidt levels: few output tiles, long K) are split along K
-    // over up to 128 CTAs; slices are summed in slice order by a second kernel, so the result stays deterministic
+    // products with at least a 64 x 64 result go to the fp64 tensor cores (128 x 128 tiles); thinner ones (the bottom levels of
+    // the Gram-Schmidt recursion: a handful of columns against n rows) stay on the 64 x 64 SIMT kernel
+    const bool mma = M >= 64 && N >= 64 && !h->opt_spd_simt;
+    const int tile = mma ? kMmaTM : 64;
+    dim3 grid((unsigned)((N + tile - 1) / tile), (unsigned)((M + tile - 1) / tile));
+    auto launch = [&](dim3 gr) {
+        if (mma) gemm_f64_mma_kernel<<<gr, kMmaThreads, kMmaSmemBytes, h->stream>>>(g);
+        else gemm_f64_kernel<<<gr, 256, 0, h->stream>>>(g);
+    };
+    // few output tiles but a long K (Q1^T Q2 of the lower and middle Gram-Schmidt levels): split along K over up to 2 CTAs per
+    // SM worth of slices; slices are summed in slice order by a second kernel, so the result stays deterministic
     const long long tiles = (long long)grid.x * grid.y;
     if (h->gemm_ws && tiles < h->sm_count && K >= 2048 && M * N <= kGemmWsTile) {
         int slices = (int)std::min<long long>({128, K / 512, (long long)(2 * h->sm_count) / tiles});
@@ -1423,14 +1486,14 @@ int launch_gemm(lamcg *h, const double *A, const double *B, double *C, long long
             slices = (int)((K + g.k_slice - 1) / g.k_slice);
             g.ws = h->gemm_ws;
             grid.z = (unsigned)slices;
-            gemm_f64_kernel<<<grid, 256, 0, h->stream>>>(g);
+            launch(grid);
             CK(cudaGetLastError());
             gemm_splitk_reduce_kernel<<<(unsigned)std::min<long long>((M * N + 255) / 256, 1024), 256, 0, h->stream>>>(g, slices);
             CK(cudaGetLastError());
             return LAMCG_OK;
         }
     }
-    gemm_f64_kernel<<<grid, 256, 0, h->stream>>>(g);
+    launch(grid);
     CK(cudaGetLastError());
     return LAMCG_OK;
 }
@@ -1474,6 +1537,7 @@ int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
     if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "the SPD generator is fp64 only");
     int rc = alloc_system(h, n);
     if (rc != LAMCG_OK) return rc;
+    CK(cudaFuncSetAttribute(gemm_f64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes));
     double *Q = nullptr, *buf = nullptr, *d_dev = nullptr;
     auto cleanup = [&]() { cudaFree(Q); cudaFree(buf); cudaFree(d_dev); cudaFree(h->gemm_ws); h->gemm_ws = nullptr; };
     if (cudaMalloc(&h->gemm_ws, (size_t)128 * kGemmWsTile * sizeof(double)) != cudaSuccess) { cudaGetLastError(); h->gemm_ws = nullptr; }

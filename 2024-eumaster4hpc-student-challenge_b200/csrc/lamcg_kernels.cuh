@@ -1312,6 +1312,262 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
 }
 
 // =============================================================================================
+// Persistent loop, fourth generation ("gathered Ap", n <= 4096; default for n <= 2048).  Generations 1-3 follow the textbook
+// distribution of CG: every CTA owns the x, r entries of its rows, so an iteration needs TWO grid-wide scalar all-reduces (p.Ap,
+// r.r) and the publication of the new r slices (release fence + acquire polls) — at n = 2048 that was 2 x ~2.3 us of a 6.9 us
+// iteration, and neither a two-level exchange through L2 nor a thread-block-cluster first hop over DSMEM
+// (tools/cluster_exchange.cu, profiles/r02_cluster_exchange.log) shortens a hop chain that has to cross L2 once anyway.
+// This generation exchanges ONCE per iteration: the CTAs all-gather Ap itself.  Each owner thread stores its row's Ap as two
+// self-validating 8-byte words {iteration tag : 32 | half of the double : 32} (NCCL's "LL" idea: an aligned 8-byte store is
+// single-copy atomic, so a word whose tag matches carries valid data — no flag, no fence, no second trip), every thread of
+// every CTA polls the entries of ITS columns (the ones whose p it keeps in registers), and then every CTA computes p.Ap,
+// alpha, r -= alpha Ap, r.r, beta, the stop test and p = r + beta p REDUNDANTLY on the full vectors, which live distributed
+// over the registers of its 512 threads.  Same operations per element as the reference loop (OMP.hpp:68-78), fixed summation
+// orders, identical in every CTA, so all CTAs take the same branch without ever exchanging a scalar.
+//   GEMV as in the second generation: warp w owns a column segment of every row of the CTA, p slice in registers, all rows of
+//   the CTA resident in shared memory (n = 2048: 14 x 16 KB), 8 rows accumulated at once, halving butterfly.
+// =============================================================================================
+template <int LD>
+__device__ __forceinline__ void ll_load_pair(const unsigned long long *p, unsigned long long (&w)[4])
+{
+    if (LD == 0) asm volatile("ld.relaxed.gpu.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p) : "memory");
+    if (LD == 1) { asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p) : "memory");
+                   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2) : "memory"); }
+    if (LD == 2) { asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p) : "memory");
+                   asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2) : "memory"); }
+}
+
+// Sum of one value per thread over the CTA in a fixed order (lane butterfly, then the 16 warps in index order); the total is
+// returned in EVERY thread.  s_red: [kPersistThreads / 32] doubles, reusable right after the call (two barriers inside).
+__device__ __forceinline__ double persist_block_total(double v, double *s_red)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    v = warp_sum(v);
+    if (lane == 0) s_red[warp] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < 512 / 32; ++w) s = __dadd_rn(s, s_red[w]);
+    __syncthreads();
+    return s;
+}
+
+template <int PL, int LD>
+__global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
+{
+    extern __shared__ __align__(16) double psm[];
+    constexpr int NT = 512, NW = NT / 32;
+    constexpr int K2 = PL / 2;   // column pairs (16-byte loads of A, 32-byte tagged entries of Ap) per lane
+    constexpr int SEG = 32 * PL; // columns per warp
+    constexpr unsigned FULL = 0xffffffffu;
+    const int n = (int)a.n, lda = (int)a.lda;
+    double *arows = psm;                              // [rows_smem][lda] resident rows of A
+    double *part = psm + (size_t)a.rows_smem * lda;   // [NW][rows_max rounded up to 8] per-warp row partials
+    __shared__ double s_red[NW];
+    __shared__ double s_bcast;
+    __shared__ double s_scal[4]; // alpha | beta | rr | stop code
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int G = gridDim.x, bid = blockIdx.x;
+    const int base = n / G, rem = n % G;
+    const int r0 = bid * base + (bid < rem ? bid : rem);
+    const int rcnt = base + (bid < rem ? 1 : 0);
+    const int cbase = warp * SEG + 2 * lane; // this lane's columns: cbase + 64 k + {0, 1}
+    const int rows_pad = (a.rows_max + 7) & ~7;
+    DevState *st = a.st;
+
+    // ---- init: p = r = b in registers (b is zero padded to lda), own x = 0, bb = b.b (same order in every CTA)
+    double preg[PL], rreg[PL];
+    double local = 0.0;
+#pragma unroll
+    for (int k = 0; k < K2; ++k) {
+        const int c = cbase + 64 * k;
+        double2 bv = make_double2(0.0, 0.0);
+        if (c < lda) bv = *reinterpret_cast<const double2 *>(a.b + c);
+        preg[2 * k] = rreg[2 * k] = bv.x;
+        preg[2 * k + 1] = rreg[2 * k + 1] = bv.y;
+        local = mul_add(bv.x, bv.x, local);
+        local = mul_add(bv.y, bv.y, local);
+    }
+    const double bb = persist_block_total(local, s_red);
+    double x_own = 0.0, r_own = 0.0, p_own = 0.0, Ap_own = 0.0; // the owner thread's copies of its row's entries
+    if (tid < rcnt) r_own = p_own = a.b[r0 + tid];
+    const int nres = rcnt < a.rows_smem ? rcnt : a.rows_smem;
+    {
+        const double *src = a.A + (size_t)r0 * lda;
+        for (int i = 2 * tid; i < nres * lda; i += 2 * NT)
+            *reinterpret_cast<double2 *>(arows + i) = __ldg(reinterpret_cast<const double2 *>(src + i));
+    }
+    __syncthreads();
+
+    double rr = bb, beta = 0.0;
+    int it;
+    bool converged = false, broke = false;
+    long long ph[6] = {0, 0, 0, 0, 0, 0}; // p update | GEMV | row sums + publish | gather Ap | p.Ap, alpha, r, r.r | beta, stop test
+    long long tc = clock64();
+#define LAMCG_PHASE(k) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; }
+    for (it = 1; it <= a.max_iters; ++it) {
+        if (it > 1) { // p = r + beta p on the register slices (axpby(1.0, r, beta, p), OMP.hpp:78)
+#pragma unroll
+            for (int k = 0; k < PL; ++k) preg[k] = __dadd_rn(rreg[k], __dmul_rn(beta, preg[k]));
+            if (tid < rcnt) p_own = __dadd_rn(r_own, __dmul_rn(beta, p_own));
+        }
+        LAMCG_PHASE(0)
+        // ---- GEMV: 8 rows at a time over this warp's column segment
+        for (int g0 = 0; g0 < rcnt; g0 += 8) {
+            double acc[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                acc[j] = 0.0;
+                const int row = g0 + j;
+                if (row < nres) {
+                    const double *arow = arows + row * lda;
+#pragma unroll
+                    for (int k = 0; k < K2; ++k) {
+                        const int c = cbase + 64 * k;
+                        if (c < lda) {
+                            const double2 av = *reinterpret_cast<const double2 *>(arow + c);
+                            acc[j] = mul_add(av.x, preg[2 * k], acc[j]);
+                            acc[j] = mul_add(av.y, preg[2 * k + 1], acc[j]);
+                        }
+                    }
+                } else if (row < rcnt) {
+                    const double *arow = a.A + (size_t)(r0 + row) * lda;
+#pragma unroll
+                    for (int k = 0; k < K2; ++k) {
+                        const int c = cbase + 64 * k;
+                        if (c < lda) {
+                            const double2 av = __ldg(reinterpret_cast<const double2 *>(arow + c));
+                            acc[j] = mul_add(av.x, preg[2 * k], acc[j]);
+                            acc[j] = mul_add(av.y, preg[2 * k + 1], acc[j]);
+                        }
+                    }
+                }
+            }
+            // halving butterfly: each kept value is computed by exactly one lane (see the second generation)
+            const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
+            double v4[4], v2[2];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const double keep = b4 ? acc[4 + i] : acc[i], send = b4 ? acc[i] : acc[4 + i];
+                v4[i] = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 16));
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const double keep = b3 ? v4[2 + i] : v4[i], send = b3 ? v4[i] : v4[2 + i];
+                v2[i] = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 8));
+            }
+            double v = __dadd_rn(b2 ? v2[1] : v2[0], __shfl_xor_sync(FULL, b2 ? v2[0] : v2[1], 4));
+            v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2));
+            v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1));
+            if ((lane & 3) == 0) part[warp * rows_pad + g0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = v;
+        }
+        __syncthreads();
+        LAMCG_PHASE(1)
+        // ---- the owner of a row adds its 16 warp partials in warp order and publishes the row's Ap as two tagged words
+        unsigned long long *ll = a.ll + (size_t)(it & 1) * 2 * (size_t)lda; // double-buffered by iteration parity (WAR: see below)
+        const unsigned long long tag = (unsigned long long)(unsigned int)it << 32;
+        if (tid < rcnt) {
+            double sum = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, part[w * rows_pad + tid]);
+            Ap_own = sum;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(sum);
+            st_relaxed_gpu_v2u64(ll + 2 * (size_t)(r0 + tid), tag | (bits >> 32), tag | (bits & 0xffffffffull));
+        }
+        LAMCG_PHASE(2)
+        // ---- all-gather: poll the entries of this thread's columns.  A CTA can run at most one iteration ahead of the slowest
+        // one (it cannot finish iteration it+1 without that CTA's words of it+1, which are stored after its polls of iteration it
+        // have completed), so two buffers are enough and a matching tag always belongs to the current iteration.
+        double ap[PL];
+        {
+            unsigned long long w[K2][4];
+            bool ok[K2];
+#pragma unroll
+            for (int k = 0; k < K2; ++k) ok[k] = cbase + 64 * k >= n; // nothing beyond n (n is even or the odd tail is handled below)
+            const long long t0 = clock64();
+            for (;;) {
+                bool all = true;
+#pragma unroll
+                for (int k = 0; k < K2; ++k)
+                    if (!ok[k]) ll_load_pair<LD>(ll + 2 * (size_t)(cbase + 64 * k), w[k]);
+#pragma unroll
+                for (int k = 0; k < K2; ++k)
+                    if (!ok[k]) {
+                        const int c = cbase + 64 * k;
+                        const bool second = c + 1 < n; // the last column pair of an odd n has only one entry
+                        ok[k] = (w[k][0] >> 32) == (tag >> 32) && (w[k][1] >> 32) == (tag >> 32) &&
+                                (!second || ((w[k][2] >> 32) == (tag >> 32) && (w[k][3] >> 32) == (tag >> 32)));
+                        all = all && ok[k];
+                    }
+                if (all) break;
+                if (clock64() - t0 > 4000000000LL) {
+                    st->error = 3;
+                    __threadfence_system();
+                    __trap();
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < K2; ++k) {
+                const int c = cbase + 64 * k;
+                ap[2 * k] = c < n ? __longlong_as_double((long long)(((w[k][0] & 0xffffffffull) << 32) | (w[k][1] & 0xffffffffull))) : 0.0;
+                ap[2 * k + 1] = c + 1 < n ? __longlong_as_double((long long)(((w[k][2] & 0xffffffffull) << 32) | (w[k][3] & 0xffffffffull))) : 0.0;
+            }
+        }
+        LAMCG_PHASE(3)
+        // ---- redundant vector work on the register slices: p.Ap, alpha, r -= alpha Ap, r.r
+        local = 0.0;
+#pragma unroll
+        for (int k = 0; k < PL; ++k) local = mul_add(preg[k], ap[k], local);
+        const double pAp = persist_block_total(local, s_red);
+        if (tid == 0) s_scal[0] = rr / pAp; // alpha = rr / (p.Ap): one division per CTA, broadcast
+        __syncthreads();
+        const double alpha = s_scal[0], nalpha = -alpha;
+        local = 0.0;
+#pragma unroll
+        for (int k = 0; k < PL; ++k) {
+            rreg[k] = __dadd_rn(__dmul_rn(nalpha, ap[k]), rreg[k]); // axpby(-alpha, Ap, 1.0, r)
+            local = mul_add(rreg[k], rreg[k], local);
+        }
+        if (tid < rcnt) {
+            x_own = __dadd_rn(__dmul_rn(alpha, p_own), x_own);       // axpby(alpha, p, 1.0, x)
+            r_own = __dadd_rn(__dmul_rn(nalpha, Ap_own), r_own);
+        }
+        const double rrn = persist_block_total(local, s_red);
+        LAMCG_PHASE(4)
+        if (tid == 0) {
+            const double rel0 = sqrt(rrn / bb);
+            s_scal[1] = rrn / rr; // beta = rr_new / rr
+            s_scal[2] = rrn;
+            const bool broke0 = !(rel0 == rel0) || isinf(rel0) || !(s_scal[1] == s_scal[1]);
+            s_scal[3] = rel0 < a.eps ? 1.0 : (broke0 ? 2.0 : 0.0);
+            if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
+        }
+        __syncthreads();
+        beta = s_scal[1];
+        rr = s_scal[2];
+        const double code = s_scal[3];
+        LAMCG_PHASE(5)
+        if (code == 1.0) { converged = true; break; }
+        if (code == 2.0) { broke = true; break; }
+        // no barrier needed here: thread 0 rewrites s_scal only after the CTA barriers of the next GEMV / block sum
+    }
+    if (tid < rcnt) a.x[r0 + tid] = x_own;
+    if (bid == 0 && tid == 0) {
+        st->bb = bb;
+        st->rr_final = rr;
+        st->iters_done = (converged || broke) ? it : (a.max_iters > 0 ? a.max_iters : 0);
+        st->converged = converged ? 1 : 0;
+        st->breakdown = broke ? 1 : 0;
+        st->max_iters = a.max_iters;
+        st->eps = a.eps;
+        st->done = 1;
+        for (int k = 0; k < 6; ++k) st->phase_cycles[k] = ph[k];
+    }
+#undef LAMCG_PHASE
+}
+
+// =============================================================================================
 // Persistent loop, third generation ("streaming", 2048 < n <= 16384): the matrix no longer fits in the shared memory of
 // the 148 SMs, so the GEMV inside the one-kernel loop is K1's CTA-wide row sweep (R rows in flight, U 16-byte streaming
 // loads per row, thread and chunk; p comes from shared memory once per chunk and is reused for the R rows), fed from

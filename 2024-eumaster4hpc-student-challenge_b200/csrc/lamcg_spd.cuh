@@ -91,6 +91,121 @@ __global__ void __launch_bounds__(256) gemm_f64_kernel(GemmArgs g)
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// The same product on the fp64 TENSOR cores (DMMA: mma.sync.m8n8k4.f64, SASS DMMA.8x8x4) — the one dense contraction of this
+// code base, hence the one place where tensor cores are legitimate.  128 x 128 output tile per 256-thread CTA,
+// 8 warps as 2 (M) x 4 (N), each warp a 64 x 32 sub-tile = 8 x 4 fragments of 8 x 8 (64 accumulator doubles per thread), K step
+// 16, operands double-buffered in shared memory as [k][m] / [k][n] with a row pitch of 132 doubles: 132 = 4 (mod 16) makes the
+// 8-byte fragment loads (lane l reads [k0 + l % 4][m0 + l / 4]) hit 16 distinct 8-byte bank pairs per half warp.  The next K
+// step's operands are fetched from global memory into registers while the current one is multiplied.  Arbitrary strides as in
+// gemm_f64_kernel; the same deterministic split-K protocol (slice z writes its partial tile to ws, summed in slice order).
+// ---------------------------------------------------------------------------------------------
+constexpr int kMmaTM = 128, kMmaTN = 128, kMmaTK = 16, kMmaPitch = 132, kMmaThreads = 256;
+constexpr size_t kMmaSmemBytes = (size_t)2 * 2 * kMmaTK * kMmaPitch * sizeof(double); // A and B, two stages each
+
+__device__ __forceinline__ void dmma_m8n8k4(double &d0, double &d1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kMmaThreads, 1) gemm_f64_mma_kernel(GemmArgs g)
+{
+    constexpr int TM = kMmaTM, TN = kMmaTN, TK = kMmaTK, P = kMmaPitch;
+    extern __shared__ __align__(16) double gsm[];
+    double *As = gsm;               // [2][TK][P]
+    double *Bs = gsm + 2 * TK * P;  // [2][TK][P]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32; // this warp's sub-tile origin inside the CTA tile
+    const int fr = lane >> 2, fc = lane & 3;               // fragment coordinates: row / column index l/4, k index l%4
+    const long long i0 = (long long)blockIdx.y * TM, j0 = (long long)blockIdx.x * TN;
+    const long long kb = g.ws ? (long long)blockIdx.z * g.k_slice : 0;
+    const long long ke = g.ws ? (kb + g.k_slice < g.K ? kb + g.k_slice : g.K) : g.K;
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+
+    // staging: TM x TK (and TK x TN) = 2048 elements per operand, 8 per thread; the index split walks the unit-stride
+    // dimension of the operand fastest across threads (coalesced global reads for every N/T combination)
+    double ra[8], rb[8];
+    auto fetch = [&](long long k0) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + e * kMmaThreads;
+            int am, ak;
+            if (g.sai == 1) { am = idx % TM; ak = idx / TM; } else { ak = idx % TK; am = idx / TK; }
+            const long long gi = i0 + am, gk = k0 + ak;
+            ra[e] = (gi < g.M && gk < ke) ? g.A[gi * g.sai + gk * g.sak] : 0.0;
+            int bn, bk;
+            if (g.sbj == 1) { bn = idx % TN; bk = idx / TN; } else { bk = idx % TK; bn = idx / TK; }
+            const long long gj = j0 + bn, gk2 = k0 + bk;
+            rb[e] = (gj < g.N && gk2 < ke) ? g.B[gk2 * g.sbk + gj * g.sbj] : 0.0;
+        }
+    };
+    auto stash = [&](int stage) {
+        double *as = As + stage * TK * P, *bs = Bs + stage * TK * P;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int idx = tid + e * kMmaThreads;
+            int am, ak;
+            if (g.sai == 1) { am = idx % TM; ak = idx / TM; } else { ak = idx % TK; am = idx / TK; }
+            as[ak * P + am] = ra[e];
+            int bn, bk;
+            if (g.sbj == 1) { bn = idx % TN; bk = idx / TN; } else { bk = idx % TK; bn = idx / TK; }
+            bs[bk * P + bn] = rb[e];
+        }
+    };
+
+    if (kb < ke) {
+        fetch(kb);
+        stash(0);
+    }
+    __syncthreads();
+    int stage = 0;
+    for (long long k0 = kb; k0 < ke; k0 += TK, stage ^= 1) {
+        const bool more = k0 + TK < ke;
+        if (more) fetch(k0 + TK); // global loads in flight while this stage is multiplied
+        const double *as = As + stage * TK * P, *bs = Bs + stage * TK * P;
+#pragma unroll
+        for (int kk = 0; kk < TK; kk += 4) {
+            double af[8], bf[4];
+#pragma unroll
+            for (int a = 0; a < 8; ++a) af[a] = as[(kk + fc) * P + wm + 8 * a + fr];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) bf[b] = bs[(kk + fc) * P + wn + 8 * b + fr];
+#pragma unroll
+            for (int a = 0; a < 8; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) dmma_m8n8k4(acc[a][b][0], acc[a][b][1], af[a], bf[b]);
+        }
+        if (more) stash(stage ^ 1); // the other stage was last read before the barrier that ended the previous step
+        __syncthreads();
+    }
+    // C fragment of m8n8k4: lane l holds row l/4, columns 2*(l%4) and 2*(l%4)+1
+#pragma unroll
+    for (int a = 0; a < 8; ++a) {
+        const long long gi = i0 + wm + 8 * a + fr;
+        if (gi >= g.M) continue;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                const long long gj = j0 + wn + 8 * b + 2 * fc + q;
+                if (gj >= g.N) continue;
+                const double v = acc[a][b][q];
+                if (g.ws) {
+                    g.ws[(long long)blockIdx.z * g.M * g.N + gi * g.N + gj] = v;
+                    continue;
+                }
+                double *c = g.C + gi * g.sci + gj * g.scj;
+                *c = g.beta == 0.0 ? g.alpha * v : fma(g.alpha, v, g.beta * *c);
+            }
+        }
+    }
+}
+
 // Second pass of a split-K product: C = alpha * (sum of the slices, in slice order) + beta * C.
 __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(GemmArgs g, int slices)
 {

@@ -63,9 +63,12 @@ typedef struct {
     int rank, nranks, device, sm_count;
     int comm_mode;      /* 0 none (single rank), 1 NCCL, 2 peer stores */
     int has_matrix, has_rhs;
-    int gemv_variant;   /* resolved GEMV kernel: 1 = ldg, 2 = tma ring */
+    int gemv_variant;   /* resolved K1 kernel: 36 / 32 row sweep with 128-bit loads (defaults: tall / short blocks), 46 / 42 the same
+                           with 256-bit loads, 11 warp-per-rows with TMA-staged p, 2 TMA ring */
     int gemv_grid, gemv_block, gemv_smem_bytes;
     int dtype;          /* 0 fp64, 1 fp32 */
+    int ingest_threads; /* reader threads and ... */
+    int ingest_chunks;  /* ... staging chunks the last lamcg_load_matrix used on this rank */
 } lamcg_info;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -85,11 +88,16 @@ const char *lamcg_last_error(const lamcg_t *h);
 const char *lamcg_version(void);
 
 /* ---- options (all optional; also readable from env LAMCG_<KEY>) ----------------------------- */
-/*  gemv_variant  0 auto | 1x ldg | 2x tma ring | 3x, 6x, 7x cta-wide row sweep (default 36 / 32)
+/*  gemv_variant  0 auto | 36 / 32 row sweep, 128-bit loads | 46 / 42 row sweep, 256-bit loads | 11 warp rows + TMA-staged p | 2 TMA ring
  *  loop_mode     0 auto (single rank, fp64, n <= 16384: 3; else 2) | 1 stream | 2 graph | 3 persistent (one cooperative kernel)
  *  persist_variant  0 auto | 1 | 2 | 3: generation of the persistent kernel (rows in shared memory / p in registers / streaming sweep)
+ *  persist_cluster  thread-block-cluster size of the persistent kernel's scalar exchange (0 auto, 1 none, 2, 4, 8)
+ *  persist_grid  upper bound on the CTAs of the persistent kernel (0: one per SM)
  *  chunk_iters   iterations per graph launch          time_gemv   0/1 event-time every GEMV (stream mode)
- *  gemv_ctas_per_sm, persist_rows_smem, ingest_threads  tuning overrides     history  0/1 keep sqrt(rr/bb) per iteration (default 1) */
+ *  ingest_threads (default 8), ingest_chunk_bytes (default 4 MB): reader threads / staging-chunk size of lamcg_load_matrix
+ *  peer_timeout_s (default 600): bound of every in-kernel wait for a peer rank; on expiry the solve returns LAMCG_ERR_DEVICE
+ *  gemv_ctas_per_sm, persist_rows_smem  tuning overrides     history  0/1 keep sqrt(rr/bb) per iteration (default 1)
+ *  debug_persist_fail  test hook: pretend the cooperative launch of the persistent kernel was refused */
 int lamcg_set_option(lamcg_t *h, const char *key, long long value);
 int lamcg_get_info(const lamcg_t *h, lamcg_info *out);
 

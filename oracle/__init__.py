@@ -266,6 +266,45 @@ def ref_gen_solve(n: int, max_iters: int, rel_error: float, threads: int | None 
     return res
 
 
+class RefGenSystem:
+    """The unmodified reference's generate-mode system kept alive between solves (``ref_gen_open`` in ref_harness.cpp):
+    generate once, ``solve(k)`` as often as needed.  Raises MemoryError when the reference cannot allocate the n x n matrix."""
+
+    def __init__(self, n: int, threads: int | None = None):
+        R = ref()
+        if threads:
+            R.ref_set_threads(threads)
+        R.ref_gen_open.restype = ctypes.c_void_p
+        R.ref_gen_open.argtypes = [ctypes.c_size_t, ctypes.POINTER(ctypes.c_double)]
+        R.ref_gen_solve_again.restype = ctypes.c_int
+        R.ref_gen_solve_again.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double, _c_double_p, ctypes.POINTER(ctypes.c_int),
+                                          ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+        R.ref_gen_close.restype = None
+        R.ref_gen_close.argtypes = [ctypes.c_void_p]
+        g = ctypes.c_double()
+        self.n, self._R = n, R
+        self._h = R.ref_gen_open(n, ctypes.byref(g))
+        self.gen_seconds = g.value
+        if not self._h:
+            raise MemoryError(f"the reference could not generate its {n} x {n} system")
+
+    def solve(self, max_iters: int, rel_error: float, want_x: bool = True) -> Result:
+        x = np.zeros(self.n) if want_x else None
+        it, rel, secs = ctypes.c_int(), ctypes.c_double(), ctypes.c_double()
+        rc = self._R.ref_gen_solve_again(self._h, max_iters, rel_error, _dp(x) if want_x else None, ctypes.byref(it), ctypes.byref(rel),
+                                         ctypes.byref(secs))
+        assert rc >= 0, "could not parse the reference's output"
+        return Result(bool(rc), it.value, rel.value, x, None, secs.value)
+
+    def close(self) -> None:
+        if self._h:
+            self._R.ref_gen_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
+
+
 def ref_omp_solve(A: np.ndarray, b: np.ndarray, max_iters: int, rel_error: float, threads: int | None = None) -> Result:
     R = ref()
     if threads:

