@@ -6,6 +6,7 @@
 #include <mutex>
 #include <thread>
 #include <cerrno>
+#include <chrono>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
@@ -82,6 +83,7 @@ struct lamcg {
     long long opt_peer_timeout_s = 600;   // bound of every peer flag wait; ranks may finish a cold-cache ingest minutes apart
     long long opt_persist_grid = 0;       // 0: one CTA per SM; k > 0: at most k CTAs in the one-kernel loop (tests: small-device behaviour)
     long long opt_debug_persist_fail = 0; // test hook: pretend the cooperative launch was refused
+    long long opt_fuse_updates = 1;       // K2 + K3 in one cooperative launch (single rank / peer mode)
     long long opt_spd_simt = 0;           // 1: the SPD generator's products on the SIMT kernel only (comparison / fallback)
     int clock_khz = 1965000;
     char *ingest_pool = nullptr;          // pinned staging buffers of the file ingest (kept between loads)
@@ -90,6 +92,7 @@ struct lamcg {
     long long last_ingest_chunks = 0;
     long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
     long long opt_persist_variant = 0;    // 0 auto (fourth generation for n <= 2048, first below 4096, third from there) | 1 first | 2 second (n <= 4096) | 3 third | 4 fourth (n <= 4096)
+    long long opt_persist_ll_copies = 0;  // generation 4: replicas of the gathered-Ap array (0 = auto: ~2048 entries in total)
     long long opt_persist_poll = 0;       // generation 4: polling load of the gathered Ap: 0 ld.relaxed.gpu.v4.u64 | 1 ld.relaxed.gpu.v2.u64 x2 | 2 ld.cg.v2.u64 x2
 
     // comm
@@ -333,8 +336,11 @@ int launch_gemv(lamcg *h, int check_done, int par = 0)
 int vec_grid(lamcg *h)
 {
     size_t want = (h->local_rows + kVecThreads - 1) / kVecThreads;
-    return (int)std::min<size_t>(std::max<size_t>(want, 1), (size_t)h->sm_count * 4);
+    return (int)std::min<size_t>(std::max<size_t>(want, 1), (size_t)h->sm_count * 4); // 4 CTAs of 256 threads per SM: always co-resident
 }
+
+// K2 and K3 as one cooperative launch unless NCCL has to run between them (or option fuse_updates = 0)
+bool fuse_updates(const lamcg *h) { return h->comm_mode != kCommNccl && h->opt_fuse_updates != 0; }
 
 VecArgs vec_args(lamcg *h, int par)
 {
@@ -354,6 +360,7 @@ VecArgs vec_args(lamcg *h, int par)
     v.rows = (long long)h->local_rows;
     v.row_offset = (long long)h->row_offset;
     v.par = par;
+    v.fused = fuse_updates(h) ? 1 : 0;
     return v;
 }
 
@@ -385,6 +392,13 @@ int enqueue_iteration(lamcg *h, int par, cudaEvent_t ev0, cudaEvent_t ev1, int *
         NCK(N.AllReduce(&h->st->pAp_local, &h->st->pAp, 1, ncclDouble, ncclSum, h->nccl, h->stream));
     VecArgs v = vec_args(h, par);
     const int vg = vec_grid(h);
+    if (v.fused) {
+        void *params[] = {&v};
+        const void *fn = h->dtype == 0 ? (const void *)update_fused_kernel<double> : (const void *)update_fused_kernel<float>;
+        CK(cudaLaunchCooperativeKernel(fn, dim3(vg), dim3(kVecThreads), params, 0, h->stream));
+        *launches += 2;
+        return LAMCG_OK;
+    }
     if (h->dtype == 0) update_xr_kernel<double><<<vg, kVecThreads, 0, h->stream>>>(v);
     else update_xr_kernel<float><<<vg, kVecThreads, 0, h->stream>>>(v);
     CK(cudaGetLastError());
@@ -457,7 +471,10 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
     if (h->opt_persist_grid > 0) grid = (int)std::min<long long>(grid, h->opt_persist_grid);
     // generations 1-3: [2][G][G][kLLStride] tagged scalar words; generation 4: [2][lda][2] tagged entries of the gathered Ap
-    const size_t ll_words = std::max((size_t)2 * kLLStride * grid * grid, (size_t)4 * h->lda);
+    // replicas of the gathered vector: two from n = 1024 up, about 2048 entries in total below
+    int ll_copies = h->lda >= 1024 ? 2 : (int)std::min<size_t>(8, 2048 / std::max<size_t>(h->lda, 1)); // measured: profiles/r02_gen4_probe.log
+    if (h->opt_persist_ll_copies > 0) ll_copies = (int)std::min<long long>(h->opt_persist_ll_copies, 64);
+    const size_t ll_words = std::max((size_t)2 * kLLStride * grid * grid, (size_t)4 * h->lda * ll_copies);
     if (!h->persist_ll || h->persist_ll_words < ll_words) {
         cudaFree(h->persist_ll);
         h->persist_ll = nullptr;
@@ -476,7 +493,10 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     // persist_variant: 0 auto | 1 first generation (row tasks) | 2 second (p in registers, all rows in shared memory; n <= 4096;
     // auto for n <= 2048) | 3 third (K1's streaming row sweep inside the loop; auto above)
     const bool v2_ok = h->lda <= 4096;
-    const bool v4 = v2_ok && (h->opt_persist_variant == 4 || (h->opt_persist_variant == 0 && h->lda <= 2048));
+    // auto: the one-exchange generation wherever p fits the register slices and beats the streaming sweep (measured,
+    // profiles/r02_small_n_gen4.log: n = 2048 207 k it/s vs 145 k for the second generation, n = 3000 98 k vs 88 k for the first;
+    // at n = 4096 the third generation's 37.9 k wins over 35.9 k)
+    const bool v4 = v2_ok && (h->opt_persist_variant == 4 || (h->opt_persist_variant == 0 && h->lda < 4096));
     const bool v2 = v2_ok && h->opt_persist_variant == 2;
     // auto above lda = 2048: up to lda < 4096 the first generation still keeps a useful share of the rows in shared memory
     // (n = 3000: 87.7 k it/s vs 72.9 k for the streaming sweep; equal at 4096), beyond that the sweep wins (n = 8192: 12.2 k vs 9.9 k)
@@ -538,6 +558,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     a.segs = segs;
     a.rows_smem = rows_smem;
     a.rows_max = rows_max;
+    a.ll_copies = ll_copies;
     CK(cudaMemsetAsync(h->persist_ll, 0, ll_words * sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->st, 0, sizeof(DevState), h->stream));
     CK(cudaEventRecord(h->ev_start, h->stream));
@@ -665,7 +686,7 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
         if (loop_mode == kLoopGraph && (launched & 1) == 0) {
             CK(cudaGraphLaunch(h->graph_exec, h->stream)); // the captured chunk starts on parity 0
             launched += chunk;
-            launches += 3 * chunk;
+            launches += (fuse_updates(h) ? 2 : 3) * chunk;
         } else {
             const int count = loop_mode == kLoopGraph ? 1 : chunk; // graph loop resumed on an odd iteration: one plain step first
             for (int i = 0; i < count && launched < max_total; ++i, ++launched) {
@@ -824,6 +845,7 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
     h->opt_persist_variant = env_ll("persist_variant", 0);
     h->opt_persist_poll = env_ll("persist_poll", 0);
+    h->opt_fuse_updates = env_ll("fuse_updates", 1);
     h->opt_ingest_threads = env_ll("ingest_threads", 8);
     h->opt_ingest_chunk_bytes = env_ll("ingest_chunk_bytes", 4ll << 20);
     h->opt_peer_timeout_s = env_ll("peer_timeout_s", 600);
@@ -888,12 +910,14 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "persist_rows_smem") h->opt_persist_rows_smem = value;
     else if (k == "persist_variant") h->opt_persist_variant = value;
     else if (k == "persist_poll") h->opt_persist_poll = value;
+    else if (k == "persist_ll_copies") h->opt_persist_ll_copies = value;
     else if (k == "ingest_threads") h->opt_ingest_threads = value;
     else if (k == "ingest_chunk_bytes") h->opt_ingest_chunk_bytes = value;
     else if (k == "peer_timeout_s") { h->opt_peer_timeout_s = value; h->pv.timeout_cycles = peer_timeout_cycles(h); }
     else if (k == "persist_grid") h->opt_persist_grid = value;
     else if (k == "debug_persist_fail") h->opt_debug_persist_fail = value;
     else if (k == "spd_simt") h->opt_spd_simt = value;
+    else if (k == "fuse_updates") h->opt_fuse_updates = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->alloc_n) {
@@ -1520,6 +1544,91 @@ int gram_schmidt(lamcg *h, double *Q, long long n, long long c0, long long c1, d
     return gram_schmidt(h, Q, n, mid, c1, buf);
 }
 
+// ---- glibc rand() restated (stdlib/random_r.c, TYPE_3): srand(seed) fills r[0..30] with the Park-Miller minimal standard
+// generator, discards 310 outputs of v[k] = v[k-3] + v[k-31]; rand() returns v[k] >> 1.  State here: the 31 elements preceding
+// the next output, oldest first.
+struct GlibcState { uint32_t v[31]; };
+
+GlibcState glibc_srand(unsigned seed)
+{
+    int32_t r[31];
+    if (seed == 0) seed = 1;
+    r[0] = (int32_t)seed;
+    for (int i = 1; i < 31; ++i) {
+        const long hi = r[i - 1] / 127773, lo = r[i - 1] % 127773;
+        long w = 16807 * lo - 2836 * hi;
+        if (w < 0) w += 2147483647;
+        r[i] = (int32_t)w;
+    }
+    // glibc keeps a ring with the front pointer at r[3] and the rear at r[0]: element k of the linear sequence is r[(k + 3) % 31]
+    GlibcState s;
+    for (int k = 0; k < 31; ++k) s.v[k] = (uint32_t)r[(k + 3) % 31];
+    for (int i = 0; i < 310; ++i) { // one step: drop the oldest, append oldest + (element 28)
+        const uint32_t nv = s.v[0] + s.v[28];
+        for (int k = 0; k < 30; ++k) s.v[k] = s.v[k + 1];
+        s.v[30] = nv;
+    }
+    return s;
+}
+
+// States at positions 0, chunk, 2 chunk, ... of the stream (nchunks x 31 words) by jump-ahead: M^chunk from repeated squaring of the
+// companion matrix of the recurrence (arithmetic mod 2^32 is what uint32_t does).
+std::vector<uint32_t> glibc_states(unsigned seed, long long chunk, long long nchunks)
+{
+    using Mat = std::vector<uint32_t>; // 31 x 31, row major
+    auto mul = [](const Mat &A, const Mat &B) {
+        Mat C(31 * 31, 0u);
+        for (int i = 0; i < 31; ++i)
+            for (int k = 0; k < 31; ++k) {
+                const uint32_t a = A[i * 31 + k];
+                if (a == 0u) continue;
+                for (int j = 0; j < 31; ++j) C[i * 31 + j] += a * B[k * 31 + j];
+            }
+        return C;
+    };
+    Mat M(31 * 31, 0u), P(31 * 31, 0u);
+    for (int i = 0; i < 30; ++i) M[i * 31 + i + 1] = 1u; // shift
+    M[30 * 31 + 0] = 1u;                                  // new element = element 0 + element 28
+    M[30 * 31 + 28] = 1u;
+    for (int i = 0; i < 31; ++i) P[i * 31 + i] = 1u;
+    for (long long e = chunk; e > 0; e >>= 1) {
+        if (e & 1) P = mul(P, M);
+        M = mul(M, M);
+    }
+    std::vector<uint32_t> out((size_t)nchunks * 31);
+    GlibcState s = glibc_srand(seed);
+    for (long long c = 0; c < nchunks; ++c) {
+        memcpy(&out[(size_t)c * 31], s.v, sizeof s.v);
+        GlibcState nx;
+        for (int i = 0; i < 31; ++i) {
+            uint32_t acc = 0u;
+            for (int k = 0; k < 31; ++k) acc += P[i * 31 + k] * s.v[k];
+            nx.v[i] = acc;
+        }
+        s = nx;
+    }
+    return out;
+}
+
+// out[0 .. count) <- the first `count` values 2*rand()/RAND_MAX - 1 after srand(seed), produced on the device
+int device_random_fill(lamcg *h, double *out, long long count, int seed)
+{
+    const long long chunk = 31 * 128; // a multiple of the ring length
+    const long long nchunks = (count + chunk - 1) / chunk;
+    const std::vector<uint32_t> states = glibc_states((unsigned)seed, chunk, nchunks);
+    unsigned int *d_states = nullptr;
+    CK(cudaMalloc(&d_states, states.size() * sizeof(uint32_t)));
+    cudaError_t e = cudaMemcpyAsync(d_states, states.data(), states.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+        glibc_rand_fill_kernel<<<(unsigned)((nchunks + 127) / 128), 128, 0, h->stream>>>(out, count, d_states, chunk);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(d_states);
+    if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "device random fill failed: %s", cudaGetErrorString(e));
+    return LAMCG_OK;
+}
+
 // random_spd_system.cpp:27-38 — glibc stream, column-major fill
 void host_random_fill(double *out, size_t count, int seed)
 {
@@ -1548,19 +1657,15 @@ int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
         cleanup();
         return h->fail(LAMCG_ERR_NOMEM, "device allocation for the %zu x %zu generator workspace failed", n, n);
     }
-    {   // Q <- U(-1,1), seed (host stream, chunked upload so host memory stays small)
-        const size_t chunk = std::min<size_t>(n * n, (size_t)1 << 24);
-        std::vector<double> stage(chunk);
-        srand((unsigned)seed);
-        for (size_t off = 0; off < n * n; off += chunk) {
-            const size_t cnt = std::min(chunk, n * n - off);
-            for (size_t i = 0; i < cnt; ++i) stage[i] = ((2.0 * rand()) / RAND_MAX) - 1.0;
-            cudaError_t e = cudaMemcpy(Q + off, stage.data(), cnt * sizeof(double), cudaMemcpyHostToDevice);
-            if (e != cudaSuccess) { cleanup(); return h->fail(LAMCG_ERR_CUDA, "upload of the random matrix failed: %s", cudaGetErrorString(e)); }
-        }
-    }
+    const auto t_start = std::chrono::steady_clock::now();
+    // Q <- U(-1,1): the glibc stream of srand(seed), generated on the device (column-major fill == stream order)
+    rc = device_random_fill(h, Q, (long long)(n * n), seed);
+    if (rc != LAMCG_OK) { cleanup(); return rc; }
+    const auto t_fill = std::chrono::steady_clock::now();
     rc = gram_schmidt(h, Q, (long long)n, 0, (long long)n, buf);
     if (rc != LAMCG_OK) { cleanup(); return rc; }
+    if (env_ll("spd_verbose", 0)) cudaStreamSynchronize(h->stream);
+    const auto t_gs = std::chrono::steady_clock::now();
     {   // eigenvalues exp(3.5 U), seed - 10 ; scale column c by sqrt(D[c])
         std::vector<double> d(n);
         host_random_fill(d.data(), n, seed - 10);
@@ -1575,9 +1680,14 @@ int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
     rc = launch_gemm(h, Q, Q, reinterpret_cast<double *>(h->A), (long long)n, (long long)n, (long long)n, /*sai*/ 1, /*sak*/ (long long)n, /*sbk*/ (long long)n,
                      /*sbj*/ 1, /*sci*/ (long long)h->lda, /*scj*/ 1, 1.0, 0.0);
     cudaError_t se = cudaStreamSynchronize(h->stream);
+    const auto t_end = std::chrono::steady_clock::now();
     cleanup();
     if (rc != LAMCG_OK) return rc;
     if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "the SPD generator faulted on the device: %s", cudaGetErrorString(se));
+    if (env_ll("spd_verbose", 0))
+        fprintf(stderr, "lamcg_random_spd_system n=%zu: random fill %.3f s, Gram-Schmidt %.3f s, scale + Y Y^T %.3f s\n", n,
+                std::chrono::duration<double>(t_fill - t_start).count(), std::chrono::duration<double>(t_gs - t_fill).count(),
+                std::chrono::duration<double>(t_end - t_gs).count());
     h->has_matrix = true;
     std::vector<double> b(n);
     host_random_fill(b.data(), n, seed + 10); // random_spd_system.cpp:166

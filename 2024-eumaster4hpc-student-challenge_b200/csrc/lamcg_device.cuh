@@ -31,11 +31,12 @@ struct DevState {
     int converged;
     int breakdown;     // stopped on a non-finite residual / beta
     int iters_done;
-    int error;         // 0 ok | 1 mbarrier timeout | 2 peer-flag timeout | 3 persistent-loop exchange timeout
+    int error;         // 0 ok | 1 mbarrier timeout | 2 peer-flag timeout | 3 persistent-loop exchange timeout | 4 fused K2+K3 wait timeout
     int hist_cap;
     unsigned int ticket_gemv;
     unsigned int ticket_xr;
     unsigned int ticket_misc;
+    unsigned int rrn_ready;      // fused K2+K3, single rank: iteration number whose r.r total is in rrn_local
     unsigned long long seq_base; // peer mode: flags published by this solve are seq_base + iteration index
     long long phase_cycles[8];   // persistent loop, CTA 0: SM cycles spent per phase (see lamcg_get_loop_profile)
 };
@@ -81,6 +82,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned 
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ unsigned int ld_acquire_gpu_u32(const unsigned int *p)
+{
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned int *p, unsigned int v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 __device__ __forceinline__ void st_release_sys_u64(unsigned long long *p, unsigned long long v)
 {
@@ -326,7 +337,8 @@ __device__ __forceinline__ double block_sum(double v, double *scratch /* >= 32 d
 // Called by ONE full warp per CTA.  which: 0 = p.Ap (K1), 1 = r.r (K2).
 __device__ __forceinline__ void grid_sum_publish(double cta_partial, double *partials, unsigned int *ticket,
                                                  double *total_out, int lane, const PeerView *pv = nullptr, int which = 0,
-                                                 int par = 0, unsigned long long seq = 0)
+                                                 int par = 0, unsigned long long seq = 0, unsigned int *ready = nullptr,
+                                                 unsigned int ready_value = 0)
 {
     const int G = gridDim.x, bid = blockIdx.x;
     int last = 0;
@@ -344,6 +356,7 @@ __device__ __forceinline__ void grid_sum_publish(double cta_partial, double *par
         if (lane == 0) {
             *total_out = s;
             *ticket = 0u;
+            if (ready) st_release_gpu_u32(ready, ready_value); // fused K2+K3: the CTAs of this grid are spinning on it
         }
         if (pv && pv->nranks > 1 && lane < pv->nranks) {
             PeerHeader *dst = peer_hdr(*pv, lane);

@@ -504,27 +504,26 @@ struct VecArgs {
     double *hist;           // [hist_cap] sqrt(rr/bb) per iteration (nullable)
     long long rows, row_offset;
     int par;                // iteration parity for the double-buffered scalars
+    int fused;              // 1: launched as update_fused_kernel (K2's last CTA also releases st->rrn_ready)
     PeerView pv;            // pv.nranks <= 1: no peer exchange
 };
 
+// Body of K2.  Returns false (in all threads) when a peer flag wait timed out: the caller leaves the kernel.
 template <typename T>
-__global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
+__device__ __forceinline__ bool xr_phase(const VecArgs &v, double *scratch /* 32 */, double *s_pAp)
 {
-    __shared__ double scratch[32];
-    __shared__ double s_pAp;
     DevState *st = v.st;
     T *vx = static_cast<T *>(v.x), *vr = static_cast<T *>(v.r);
     const T *vAp = static_cast<const T *>(v.Ap);
-    if (ld_volatile_int(&st->done)) return;
     unsigned long long seq = 0ull;
     double pAp;
     if (v.pv.nranks > 1) { // peer mode: the all-reduce of p.Ap is a wait on nranks flags + a fixed-order sum
         seq = st->seq_base + (unsigned long long)st->iter[v.par] + 1ull;
         PeerHeader *me = peer_hdr(v.pv, v.pv.me);
-        if (!peer_wait_all(me->pap_flag, v.pv.nranks, seq, st, v.pv.timeout_cycles)) return;
-        if (threadIdx.x == 0) s_pAp = peer_sum_slots(me->pap_slot[v.par], v.pv.nranks);
+        if (!peer_wait_all(me->pap_flag, v.pv.nranks, seq, st, v.pv.timeout_cycles)) return false;
+        if (threadIdx.x == 0) *s_pAp = peer_sum_slots(me->pap_slot[v.par], v.pv.nranks);
         __syncthreads();
-        pAp = s_pAp;
+        pAp = *s_pAp;
     } else {
         pAp = *v.pAp_src;
     }
@@ -542,8 +541,19 @@ __global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
     const double cta = block_sum(local, scratch);
     if (threadIdx.x < 32) {
         if (blockIdx.x == 0 && threadIdx.x == 0) st->alpha_last = alpha;
-        grid_sum_publish(cta, v.partials, &st->ticket_xr, &st->rrn_local, threadIdx.x, &v.pv, 1, v.par, seq);
+        grid_sum_publish(cta, v.partials, &st->ticket_xr, &st->rrn_local, threadIdx.x, &v.pv, 1, v.par, seq, v.fused ? &st->rrn_ready : nullptr,
+                         (unsigned int)(st->iter[v.par] + 1));
     }
+    return true;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) update_xr_kernel(VecArgs v)
+{
+    __shared__ double scratch[32];
+    __shared__ double s_pAp;
+    if (ld_volatile_int(&v.st->done)) return;
+    xr_phase<T>(v, scratch, &s_pAp);
 }
 
 // p = r + beta p on this rank's rows: the second half of K3, also run on its own by resume_kernel.
@@ -590,24 +600,22 @@ __device__ __forceinline__ void p_update(const VecArgs &v, double beta, int it, 
 // The p update is skipped on the final iteration (converged — as in the reference, which breaks
 // before it — or max_iters reached, where nobody reads p again).
 // =============================================================================================
+// Body of K3.  rr_ready: the caller has already waited for r.r (fused kernel, single rank) — read it with a volatile load.
 template <typename T>
-__global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
+__device__ __forceinline__ void p_phase(const VecArgs &v, double *s_rrn, int *s_last)
 {
-    __shared__ double s_rrn;
-    __shared__ int s_last;
     DevState *st = v.st;
-    if (ld_volatile_int(&st->done)) return;
     const int it0 = st->iter[v.par];
     double rr_new;
     if (v.pv.nranks > 1) {
         const unsigned long long seq = st->seq_base + (unsigned long long)it0 + 1ull;
         PeerHeader *me = peer_hdr(v.pv, v.pv.me);
         if (!peer_wait_all(me->rrn_flag, v.pv.nranks, seq, st, v.pv.timeout_cycles)) return;
-        if (threadIdx.x == 0) s_rrn = peer_sum_slots(me->rrn_slot[v.par], v.pv.nranks);
+        if (threadIdx.x == 0) *s_rrn = peer_sum_slots(me->rrn_slot[v.par], v.pv.nranks);
         __syncthreads();
-        rr_new = s_rrn;
+        rr_new = *s_rrn;
     } else {
-        rr_new = *v.rrn_src;
+        rr_new = *reinterpret_cast<const volatile double *>(v.rrn_src);
     }
     const double rr_old = st->rr[v.par];
     const double beta = rr_new / rr_old;
@@ -620,7 +628,7 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
     const bool broke = !(rel == rel) || isinf(rel) || !(beta == beta);
     const bool fin = conv || broke || it >= st->max_iters;
 
-    if (!fin) p_update<T>(v, beta, it, &s_last);
+    if (!fin) p_update<T>(v, beta, it, s_last);
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->rr[v.par ^ 1] = rr_new;
         st->iter[v.par ^ 1] = it;
@@ -635,6 +643,53 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
             st->done = 1;
         }
     }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
+{
+    __shared__ double s_rrn;
+    __shared__ int s_last;
+    if (ld_volatile_int(&v.st->done)) return;
+    p_phase<T>(v, &s_rrn, &s_last);
+}
+
+// =============================================================================================
+// K2 + K3 in ONE cooperative launch (single rank and peer mode; NCCL mode needs the stream between them for its all-reduce):
+// x, r update and the r.r partials, then every CTA waits until r.r is complete — single rank: the CTA that drew the last ticket
+// releases st->rrn_ready = iteration; peer mode: the nranks flags of the fused exchange, as K3 did at its start — and goes on with
+// beta, the stop test and p = r + beta p.  One launch (and its gap on the stream) fewer per iteration; the launch is cooperative
+// because every CTA spins on a value that the last CTA of the same grid produces, so all of them must be resident.
+// =============================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) update_fused_kernel(VecArgs v)
+{
+    __shared__ double scratch[32];
+    __shared__ double s_scalar;
+    __shared__ int s_last;
+    DevState *st = v.st;
+    if (ld_volatile_int(&st->done)) return;
+    if (!xr_phase<T>(v, scratch, &s_scalar)) return;
+    if (v.pv.nranks <= 1) {
+        const unsigned int want = (unsigned int)(st->iter[v.par] + 1);
+        int failed = 0;
+        if (threadIdx.x == 0) {
+            const long long t0 = clock64();
+            while (ld_acquire_gpu_u32(&st->rrn_ready) != want) {
+                if (clock64() - t0 > 4000000000LL) { // ~2 s: the grid is co-resident (cooperative launch), so this is a bug trap, not a wait
+                    failed = 1;
+                    break;
+                }
+            }
+            if (failed) {
+                st->error = 4;
+                __threadfence();
+                st->done = 1;
+            }
+        }
+        if (__syncthreads_or(failed)) return;
+    }
+    p_phase<T>(v, &s_scalar, &s_last);
 }
 
 // Continue a solve that stopped on max_iters (lamcg_solve_resume): K3 skipped the p update of its last
@@ -741,6 +796,7 @@ __global__ void __launch_bounds__(1024) init_solve_kernel(InitArgs a)
         st->error = 0;
         st->hist_cap = a.hist_cap;
         st->ticket_gemv = st->ticket_xr = st->ticket_misc = 0u;
+        st->rrn_ready = 0u;
         st->seq_base = a.seq_base;
     }
 }
@@ -836,6 +892,7 @@ struct PersistArgs {
     int segs;          // column segments per row (rows*segs tasks are dealt to the warps)
     int rows_smem;     // the first rows_smem rows of every CTA's block stay resident in shared memory
     int rows_max;      // max rows per CTA (sizes the task-partial array)
+    int ll_copies;     // generation 4: replicas of the gathered-Ap array (CTA c polls replica c % ll_copies)
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
@@ -1465,15 +1522,35 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
         __syncthreads();
         LAMCG_PHASE(1)
         // ---- the owner of a row adds its 16 warp partials in warp order and publishes the row's Ap as two tagged words
-        unsigned long long *ll = a.ll + (size_t)(it & 1) * 2 * (size_t)lda; // double-buffered by iteration parity (WAR: see below)
+        // layout [iteration parity][replica][lda][2 words]: double-buffered by parity (WAR: see below); small systems are
+        // replicated so that the 148 polling CTAs spread over more L2 lines instead of hammering n/8 of them (measured,
+        // profiles/r02_gen4_probe.log: n = 2048 180 k it/s with one replica, 218 k with two; n = 512 201 k -> 240 k with four)
+        const size_t rep_words = 2 * (size_t)lda;
+        unsigned long long *llw = a.ll + (size_t)(it & 1) * a.ll_copies * rep_words;
+        const unsigned long long *ll = llw + (size_t)(bid % a.ll_copies) * rep_words;
         const unsigned long long tag = (unsigned long long)(unsigned int)it << 32;
         if (tid < rcnt) {
             double sum = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, part[w * rows_pad + tid]);
             Ap_own = sum;
-            const unsigned long long bits = (unsigned long long)__double_as_longlong(sum);
-            st_relaxed_gpu_v2u64(ll + 2 * (size_t)(r0 + tid), tag | (bits >> 32), tag | (bits & 0xffffffffull));
+        }
+        if (a.ll_copies <= 4) { // the common case (n >= 512): the owner stores its row's two words into every replica itself
+            if (tid < rcnt) {
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(Ap_own);
+                const unsigned long long w0 = tag | (bits >> 32), w1 = tag | (bits & 0xffffffffull);
+                for (int copy = 0; copy < a.ll_copies; ++copy) st_relaxed_gpu_v2u64(llw + (size_t)copy * rep_words + 2 * (size_t)(r0 + tid), w0, w1);
+            }
+        } else { // many replicas of a tiny system: rcnt rows x ll_copies replicas, one store per thread; the values travel through
+                 // part[0 .. rcnt), which is dead by now (each owner has read, and now overwrites, only its own column of warp 0's partials)
+            if (tid < rcnt) part[tid] = Ap_own;
+            __syncthreads();
+            for (int e = tid; e < rcnt * a.ll_copies; e += NT) {
+                const int row = e % rcnt, copy = e / rcnt;
+                const unsigned long long bits = (unsigned long long)__double_as_longlong(part[row]);
+                st_relaxed_gpu_v2u64(llw + (size_t)copy * rep_words + 2 * (size_t)(r0 + row), tag | (bits >> 32), tag | (bits & 0xffffffffull));
+            }
+            __syncthreads(); // part is rewritten by the next GEMV
         }
         LAMCG_PHASE(2)
         // ---- all-gather: poll the entries of this thread's columns.  A CTA can run at most one iteration ahead of the slowest

@@ -219,6 +219,33 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(GemmArgs g, int
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// glibc's rand() stream on the device.  random_spd_system.cpp:27-38 fills the n x n matrix with 2*rand()/RAND_MAX - 1 after
+// srand(seed); calling rand() n^2 times on the host costs ~25 ns each (a lock per call: 6-7 s at n = 16384, most of the
+// generator's time in round 1).  glibc's default generator (TYPE_3, stdlib/random_r.c) is the additive feedback recurrence
+//     v[k] = v[k-3] + v[k-31]  (mod 2^32),      rand() = v[k] >> 1,
+// which is LINEAR: the host jumps ahead with powers of its 31 x 31 companion matrix and hands every thread the 31-word state at
+// the start of its chunk (lamcg.cu: glibc_states); the thread then produces its chunk sequentially.  Bit-identical to the host
+// stream (tests/test_gpu_spd_generator.py compares with the oracle's rand()-based fill).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) glibc_rand_fill_kernel(double *out, long long count, const unsigned int *states, long long chunk)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long first = t * chunk;
+    if (first >= count) return;
+    unsigned int v[31]; // v[j] = element k + j of the sequence, k = position of this thread's next output minus 31
+#pragma unroll
+    for (int j = 0; j < 31; ++j) v[j] = states[t * 31 + j];
+    const long long last = first + chunk < count ? first + chunk : count;
+    for (long long i0 = first; i0 < last; i0 += 31) {
+#pragma unroll
+        for (int j = 0; j < 31; ++j) { // static ring indices: v[j] becomes element k + 31 + j = (k + j) + (k + 28 + j)
+            v[j] += v[(j + 28) % 31];
+            if (i0 + j < last) out[i0 + j] = ((2.0 * (double)(int)(v[j] >> 1)) / 2147483647.0) - 1.0;
+        }
+    }
+}
+
 // Leaf of the Gram-Schmidt recursion: x /= ||x||_2 for one column (cblas_dnrm2 + cblas_dscal).
 __global__ void __launch_bounds__(256) normalize_column_kernel(double *x, long long n)
 {
