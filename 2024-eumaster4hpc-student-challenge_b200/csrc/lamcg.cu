@@ -1522,8 +1522,11 @@ int launch_gemm(lamcg *h, const double *A, const double *B, double *C, long long
     return LAMCG_OK;
 }
 
-// random_spd_system.cpp:41-62 — recursive block Gram-Schmidt on the columns [c0, c1) of the column-major Q (ld = n)
-int gram_schmidt(lamcg *h, double *Q, long long n, long long c0, long long c1, double *buf)
+constexpr long long kSpdPanel = 32; // widest leaf handled by CholeskyQR2 instead of further recursion
+
+// random_spd_system.cpp:41-62 — recursive block Gram-Schmidt on the columns [c0, c1) of the column-major Q (ld = n); leaves of
+// up to kSpdPanel columns are orthonormalised by CholeskyQR2 (lamcg_spd.cuh: chol_inverse_kernel).  small: 2 * 32 * 32 doubles.
+int gram_schmidt(lamcg *h, double *Q, long long n, long long c0, long long c1, double *buf, double *small)
 {
     const long long cnt = c1 - c0;
     if (cnt == 1) {
@@ -1531,8 +1534,21 @@ int gram_schmidt(lamcg *h, double *Q, long long n, long long c0, long long c1, d
         CK(cudaGetLastError());
         return LAMCG_OK;
     }
+    if (cnt <= kSpdPanel && !h->opt_spd_simt) {
+        double *P = Q + c0 * n, *G = small, *Rinv = small + kSpdPanel * kSpdPanel;
+        for (int pass = 0; pass < 2; ++pass) {
+            int rc = launch_gemm(h, P, P, G, cnt, cnt, n, /*sai*/ n, /*sak*/ 1, /*sbk*/ 1, /*sbj*/ n, /*sci*/ 1, /*scj*/ cnt, 1.0, 0.0);
+            if (rc != LAMCG_OK) return rc;
+            chol_inverse_kernel<<<1, 32, 0, h->stream>>>(G, (int)cnt, Rinv);
+            CK(cudaGetLastError());
+            // in place: a 64-row tile of P is read completely (K = cnt <= 32, one column tile) before the CTA writes it back
+            rc = launch_gemm(h, P, Rinv, P, n, cnt, cnt, /*sai*/ 1, /*sak*/ n, /*sbk*/ 1, /*sbj*/ cnt, /*sci*/ 1, /*scj*/ n, 1.0, 0.0);
+            if (rc != LAMCG_OK) return rc;
+        }
+        return LAMCG_OK;
+    }
     const long long mid = (c0 + c1) / 2, n1 = mid - c0, n2 = c1 - mid;
-    int rc = gram_schmidt(h, Q, n, c0, mid, buf);
+    int rc = gram_schmidt(h, Q, n, c0, mid, buf, small);
     if (rc != LAMCG_OK) return rc;
     const double *Q1 = Q + c0 * n;
     double *Q2 = Q + mid * n;
@@ -1541,7 +1557,7 @@ int gram_schmidt(lamcg *h, double *Q, long long n, long long c0, long long c1, d
     if (rc != LAMCG_OK) return rc;
     rc = launch_gemm(h, Q1, buf, Q2, n, n2, n1, /*sai*/ 1, /*sak*/ n, /*sbk*/ 1, /*sbj*/ n1, /*sci*/ 1, /*scj*/ n, -1.0, 1.0);
     if (rc != LAMCG_OK) return rc;
-    return gram_schmidt(h, Q, n, mid, c1, buf);
+    return gram_schmidt(h, Q, n, mid, c1, buf, small);
 }
 
 // ---- glibc rand() restated (stdlib/random_r.c, TYPE_3): srand(seed) fills r[0..30] with the Park-Miller minimal standard
@@ -1647,12 +1663,12 @@ int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
     int rc = alloc_system(h, n);
     if (rc != LAMCG_OK) return rc;
     CK(cudaFuncSetAttribute(gemm_f64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes));
-    double *Q = nullptr, *buf = nullptr, *d_dev = nullptr;
-    auto cleanup = [&]() { cudaFree(Q); cudaFree(buf); cudaFree(d_dev); cudaFree(h->gemm_ws); h->gemm_ws = nullptr; };
+    double *Q = nullptr, *buf = nullptr, *d_dev = nullptr, *small = nullptr;
+    auto cleanup = [&]() { cudaFree(Q); cudaFree(buf); cudaFree(d_dev); cudaFree(small); cudaFree(h->gemm_ws); h->gemm_ws = nullptr; };
     if (cudaMalloc(&h->gemm_ws, (size_t)128 * kGemmWsTile * sizeof(double)) != cudaSuccess) { cudaGetLastError(); h->gemm_ws = nullptr; }
     const size_t half = (n + 1) / 2;
     if (cudaMalloc(&Q, n * n * sizeof(double)) != cudaSuccess || cudaMalloc(&buf, (half * half + 1) * sizeof(double)) != cudaSuccess ||
-        cudaMalloc(&d_dev, n * sizeof(double)) != cudaSuccess) {
+        cudaMalloc(&d_dev, n * sizeof(double)) != cudaSuccess || cudaMalloc(&small, 2 * kSpdPanel * kSpdPanel * sizeof(double)) != cudaSuccess) {
         cudaGetLastError();
         cleanup();
         return h->fail(LAMCG_ERR_NOMEM, "device allocation for the %zu x %zu generator workspace failed", n, n);
@@ -1662,7 +1678,7 @@ int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
     rc = device_random_fill(h, Q, (long long)(n * n), seed);
     if (rc != LAMCG_OK) { cleanup(); return rc; }
     const auto t_fill = std::chrono::steady_clock::now();
-    rc = gram_schmidt(h, Q, (long long)n, 0, (long long)n, buf);
+    rc = gram_schmidt(h, Q, (long long)n, 0, (long long)n, buf, small);
     if (rc != LAMCG_OK) { cleanup(); return rc; }
     if (env_ll("spd_verbose", 0)) cudaStreamSynchronize(h->stream);
     const auto t_gs = std::chrono::steady_clock::now();

@@ -260,6 +260,46 @@ __global__ void __launch_bounds__(256) normalize_column_kernel(double *x, long l
     for (long long i = threadIdx.x; i < n; i += blockDim.x) x[i] *= inv;
 }
 
+// Leaf PANEL of the Gram-Schmidt recursion (w <= 32 columns).  The reference recurses down to single columns
+// (random_spd_system.cpp:41-62); here the last five levels (up to 31 projections + 32 normalisations = ~125 tiny launches per
+// panel, 65 k launches at n = 16384: the generator was launch bound) are replaced by CholeskyQR2 on the n x w panel: G = P^T P,
+// G = R^T R, P <- P R^-1, twice.  The thin QR factor with a positive diagonal of R is unique, so this is the same Q that
+// Gram-Schmidt produces, up to rounding (the second pass brings the orthogonality error to the level of the working precision).
+// This kernel is the middle step: one warp, lane j owns column j of R and of R^-1 (w x w, column-major, ld = w, in and out).
+__global__ void __launch_bounds__(32) chol_inverse_kernel(const double *G, int w, double *Rinv)
+{
+    __shared__ double R[32][33]; // R[i][j], upper triangular
+    __shared__ double X[32][33]; // R^-1
+    const int j = threadIdx.x;
+    for (int i = 0; i < 32; ++i) { R[i][j] = 0.0; X[i][j] = 0.0; }
+    __syncwarp();
+    // Cholesky, row by row: R[k][k] = sqrt(G[k][k] - sum_{i<k} R[i][k]^2); R[k][j] = (G[k][j] - sum_{i<k} R[i][k] R[i][j]) / R[k][k]
+    for (int k = 0; k < w; ++k) {
+        if (j >= k && j < w) {
+            double acc = G[(size_t)j * w + k]; // G is symmetric
+            for (int i = 0; i < k; ++i) acc = fma(-R[i][k], R[i][j], acc);
+            R[k][j] = acc; // not yet divided
+        }
+        __syncwarp();
+        const double d = sqrt(R[k][k]);
+        __syncwarp();
+        if (j >= k && j < w) R[k][j] = (j == k) ? d : R[k][j] / d;
+        __syncwarp();
+    }
+    // X = R^-1 by back substitution, lane j solves R x = e_j
+    if (j < w) {
+        X[j][j] = 1.0 / R[j][j];
+        for (int i = j - 1; i >= 0; --i) {
+            double acc = 0.0;
+            for (int k = i + 1; k <= j; ++k) acc = fma(R[i][k], X[k][j], acc);
+            X[i][j] = -acc / R[i][i];
+        }
+    }
+    __syncwarp();
+    if (j < w)
+        for (int i = 0; i < w; ++i) Rinv[(size_t)j * w + i] = X[i][j];
+}
+
 // Column c of the column-major n x n matrix *= sqrt(d[c])   (cblas_dscal per column, :89-92)
 __global__ void __launch_bounds__(256) scale_columns_kernel(double *Q, const double *d, long long n)
 {

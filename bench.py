@@ -244,6 +244,7 @@ def run_b200_arm(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries exactly one JSON line; NCCL's version banner goes to stderr
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
