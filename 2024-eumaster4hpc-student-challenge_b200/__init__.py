@@ -103,6 +103,7 @@ _SIGNATURES = {
     "lamcg_checkpoint_load": (ctypes.c_int, [_vp, ctypes.c_char_p]),
     "lamcg_gemv": (ctypes.c_int, [_vp, _vp, _vp, _dp]),
     "lamcg_time_gemv": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp]),
+    "lamcg_vector_update_step": (ctypes.c_int, [_vp, ctypes.c_size_t, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double, ctypes.c_int, _dp, _dp, _dp]),
     "lamcg_get_loop_profile": (ctypes.c_int, [_vp, ctypes.POINTER(ctypes.c_longlong), ctypes.c_int]),
     "lamcg_time_stream_read": (ctypes.c_int, [_vp, ctypes.c_int, ctypes.c_int, _dp, _dp]),
 }
@@ -314,6 +315,15 @@ class Solver:
         d = ctypes.c_double()
         self._ck(self._L.lamcg_gemv(self._h, _vp(p.ctypes.data), _vp(y.ctypes.data), ctypes.byref(d)))
         return y[: self.info.local_rows], d.value
+
+    def vector_update_step(self, x, r, p, Ap, rr: float, pAp: float, fused: bool = True):
+        """K2 / K3 in isolation (test hook): returns (x_new, r_new, p_new, alpha, rr_new, beta)."""
+        x, r, p = (np.array(v, dtype=self.np_dtype).reshape(-1) for v in (x, r, p))
+        Ap = _as_array(Ap, "Ap", self.np_dtype).reshape(-1)
+        a, rn, b = ctypes.c_double(), ctypes.c_double(), ctypes.c_double()
+        self._ck(self._L.lamcg_vector_update_step(self._h, x.size, _vp(x.ctypes.data), _vp(r.ctypes.data), _vp(p.ctypes.data), _vp(Ap.ctypes.data),
+                                                  float(rr), float(pAp), int(fused), ctypes.byref(a), ctypes.byref(rn), ctypes.byref(b)))
+        return x, r, p, a.value, rn.value, b.value
 
     def time_gemv(self, warmup: int = 3, reps: int = 10) -> float:
         ms = ctypes.c_double()

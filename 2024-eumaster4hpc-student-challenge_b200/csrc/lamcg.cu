@@ -93,6 +93,8 @@ struct lamcg {
     long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
     long long opt_persist_variant = 0;    // 0 auto (fourth generation for n <= 2048, first below 4096, third from there) | 1 first | 2 second (n <= 4096) | 3 third | 4 fourth (n <= 4096)
     long long opt_persist_ll_copies = 0;  // generation 4: replicas of the gathered-Ap array (0 = auto: ~2048 entries in total)
+    long long opt_persist_publish = -1;   // generation 4: -1 auto | 0 owner stores | 1 staged through shared memory
+    long long opt_persist_poll_delay = 700, opt_persist_poll_backoff = 0; // generation 4: cycles before the first poll / ns between poll rounds
     long long opt_persist_poll = 0;       // generation 4: polling load of the gathered Ap: 0 ld.relaxed.gpu.v4.u64 | 1 ld.relaxed.gpu.v2.u64 x2 | 2 ld.cg.v2.u64 x2
 
     // comm
@@ -471,8 +473,8 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
     if (h->opt_persist_grid > 0) grid = (int)std::min<long long>(grid, h->opt_persist_grid);
     // generations 1-3: [2][G][G][kLLStride] tagged scalar words; generation 4: [2][lda][2] tagged entries of the gathered Ap
-    // replicas of the gathered vector: two from n = 1024 up, about 2048 entries in total below
-    int ll_copies = h->lda >= 1024 ? 2 : (int)std::min<size_t>(8, 2048 / std::max<size_t>(h->lda, 1)); // measured: profiles/r02_gen4_probe.log
+    // replicas of the gathered vector (option persist_ll_copies; they only helped while the polls started too early)
+    int ll_copies = 1; // with the delayed first poll one replica is best at every size (profiles/r02_gen4_delay_sweep.log)
     if (h->opt_persist_ll_copies > 0) ll_copies = (int)std::min<long long>(h->opt_persist_ll_copies, 64);
     const size_t ll_words = std::max((size_t)2 * kLLStride * grid * grid, (size_t)4 * h->lda * ll_copies);
     if (!h->persist_ll || h->persist_ll_words < ll_words) {
@@ -493,10 +495,9 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     // persist_variant: 0 auto | 1 first generation (row tasks) | 2 second (p in registers, all rows in shared memory; n <= 4096;
     // auto for n <= 2048) | 3 third (K1's streaming row sweep inside the loop; auto above)
     const bool v2_ok = h->lda <= 4096;
-    // auto: the one-exchange generation wherever p fits the register slices and beats the streaming sweep (measured,
-    // profiles/r02_small_n_gen4.log: n = 2048 207 k it/s vs 145 k for the second generation, n = 3000 98 k vs 88 k for the first;
-    // at n = 4096 the third generation's 37.9 k wins over 35.9 k)
-    const bool v4 = v2_ok && (h->opt_persist_variant == 4 || (h->opt_persist_variant == 0 && h->lda < 4096));
+    // auto: the one-exchange generation wherever p fits the register slices (n <= 4096; measured, profiles/r02_small_n_gen4_final.log:
+    // n = 2048 237 k it/s vs 145 k for the second generation, n = 3000 99 k vs 88 k for the first, n = 4096 39.5 k vs 38.0 k for the third)
+    const bool v4 = v2_ok && (h->opt_persist_variant == 4 || h->opt_persist_variant == 0);
     const bool v2 = v2_ok && h->opt_persist_variant == 2;
     // auto above lda = 2048: up to lda < 4096 the first generation still keeps a useful share of the rows in shared memory
     // (n = 3000: 87.7 k it/s vs 72.9 k for the streaming sweep; equal at 4096), beyond that the sweep wins (n = 8192: 12.2 k vs 9.9 k)
@@ -535,6 +536,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     const size_t stat = fattr.sharedSizeBytes; // static shared memory counts against the same per-block limit
     const size_t budget = (size_t)dev_smem_max > fixed + stat ? (size_t)dev_smem_max - fixed - stat : 0;
     int rows_smem = resident_rows ? (int)std::min<size_t>((size_t)rows_max, budget / (h->lda * sizeof(double))) : 0;
+    if (v4 && rows_smem < rows_max && rows_smem > 8) rows_smem &= ~7; // whole 8-row groups from one place: the straight-line GEMV path
     if (h->opt_persist_rows_smem >= 0) rows_smem = std::min(rows_smem, (int)h->opt_persist_rows_smem);
     const size_t smem = fixed + (size_t)rows_smem * h->lda * sizeof(double);
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -559,6 +561,9 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     a.rows_smem = rows_smem;
     a.rows_max = rows_max;
     a.ll_copies = ll_copies;
+    a.publish_staged = h->opt_persist_publish >= 0 ? (int)(h->opt_persist_publish != 0) : (ll_copies > 4);
+    a.poll_delay = (int)std::max<long long>(0, std::min<long long>(h->opt_persist_poll_delay, 100000));
+    a.poll_backoff = (int)std::max<long long>(0, std::min<long long>(h->opt_persist_poll_backoff, 100000));
     CK(cudaMemsetAsync(h->persist_ll, 0, ll_words * sizeof(unsigned long long), h->stream));
     CK(cudaMemsetAsync(h->st, 0, sizeof(DevState), h->stream));
     CK(cudaEventRecord(h->ev_start, h->stream));
@@ -845,6 +850,7 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
     h->opt_persist_variant = env_ll("persist_variant", 0);
     h->opt_persist_poll = env_ll("persist_poll", 0);
+    h->opt_persist_poll_delay = env_ll("persist_poll_delay", 700);
     h->opt_fuse_updates = env_ll("fuse_updates", 1);
     h->opt_ingest_threads = env_ll("ingest_threads", 8);
     h->opt_ingest_chunk_bytes = env_ll("ingest_chunk_bytes", 4ll << 20);
@@ -911,6 +917,9 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "persist_variant") h->opt_persist_variant = value;
     else if (k == "persist_poll") h->opt_persist_poll = value;
     else if (k == "persist_ll_copies") h->opt_persist_ll_copies = value;
+    else if (k == "persist_publish") h->opt_persist_publish = value;
+    else if (k == "persist_poll_delay") h->opt_persist_poll_delay = value;
+    else if (k == "persist_poll_backoff") h->opt_persist_poll_backoff = value;
     else if (k == "ingest_threads") h->opt_ingest_threads = value;
     else if (k == "ingest_chunk_bytes") h->opt_ingest_chunk_bytes = value;
     else if (k == "peer_timeout_s") { h->opt_peer_timeout_s = value; h->pv.timeout_cycles = peer_timeout_cycles(h); }
@@ -1760,6 +1769,72 @@ int lamcg_gemv(lamcg_t *h, const void *p, void *y_local, double *p_dot_y)
     if (se != cudaSuccess) return h->fail(LAMCG_ERR_DEVICE, "GEMV faulted on the device: %s", cudaGetErrorString(se));
     if (p_dot_y) *p_dot_y = h->h_st[2].pAp_local;
     return check_device_error(h, h->h_st[2]);
+}
+
+int lamcg_vector_update_step(lamcg_t *h, size_t n, void *x, void *r, void *p, const void *Ap, double rr, double pAp, int fused,
+                             double *alpha, double *rr_new, double *beta)
+{
+    if (!h || !x || !r || !p || !Ap || n == 0) return LAMCG_ERR_INVALID;
+    if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "lamcg_vector_update_step is a single-rank test hook");
+    h->resumable = false;
+    CK(cudaSetDevice(h->device));
+    const size_t bytes = n * h->esz;
+    char *dv = nullptr; // x | r | Ap | p, private to this call: the hook works without a system
+    CK(cudaMalloc(&dv, 4 * bytes));
+    auto done = [&](int rc) { cudaFree(dv); return rc; };
+    cudaError_t e = cudaMemcpyAsync(dv, x, bytes, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dv + bytes, r, bytes, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dv + 2 * bytes, Ap, bytes, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dv + 3 * bytes, p, bytes, cudaMemcpyHostToDevice, h->stream);
+    DevState s{}; // "entering the vector kernels of the first iteration"
+    s.bb = rr;
+    s.rr[0] = s.rr[1] = s.rr_final = rr;
+    s.pAp_local = s.pAp = pAp;
+    s.eps = 0.0;
+    s.max_iters = 1 << 30; // not the last iteration: K3 updates p
+    h->h_st[2] = s;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h->st, &h->h_st[2], sizeof(DevState), cudaMemcpyHostToDevice, h->stream);
+    if (e != cudaSuccess) return done(h->fail(LAMCG_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e)));
+    VecArgs v;
+    v.st = h->st;
+    v.pAp_src = &h->st->pAp_local;
+    v.rrn_src = &h->st->rrn_local;
+    v.x = dv;
+    v.r = dv + bytes;
+    v.Ap = dv + 2 * bytes;
+    v.p_in = dv + 3 * bytes;
+    v.p_out = dv + 3 * bytes;
+    v.pv = no_peer();
+    v.partials = h->partials + kMaxGrid;
+    v.hist = nullptr;
+    v.rows = (long long)n;
+    v.row_offset = 0;
+    v.par = 0;
+    v.fused = fused ? 1 : 0;
+    const int vg = (int)std::min<size_t>(std::max<size_t>((n + kVecThreads - 1) / kVecThreads, 1), (size_t)h->sm_count * 4); // vec_grid() of an n-row rank
+    if (fused) {
+        void *params[] = {&v};
+        const void *fn = h->dtype == 0 ? (const void *)update_fused_kernel<double> : (const void *)update_fused_kernel<float>;
+        e = cudaLaunchCooperativeKernel(fn, dim3(vg), dim3(kVecThreads), params, 0, h->stream);
+    } else {
+        if (h->dtype == 0) update_xr_kernel<double><<<vg, kVecThreads, 0, h->stream>>>(v);
+        else update_xr_kernel<float><<<vg, kVecThreads, 0, h->stream>>>(v);
+        if (h->dtype == 0) update_p_kernel<double><<<vg, kVecThreads, 0, h->stream>>>(v);
+        else update_p_kernel<float><<<vg, kVecThreads, 0, h->stream>>>(v);
+        e = cudaGetLastError();
+    }
+    if (e != cudaSuccess) return done(h->fail(LAMCG_ERR_CUDA, "launch of the vector kernels failed: %s", cudaGetErrorString(e)));
+    cudaMemcpyAsync(x, dv, bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(r, dv + bytes, bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(p, dv + 3 * bytes, bytes, cudaMemcpyDeviceToHost, h->stream);
+    cudaMemcpyAsync(&h->h_st[2], h->st, sizeof(DevState), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t se = cudaStreamSynchronize(h->stream);
+    if (se != cudaSuccess) return done(h->fail(LAMCG_ERR_DEVICE, "the vector kernels faulted on the device: %s", cudaGetErrorString(se)));
+    const DevState &o = h->h_st[2];
+    if (alpha) *alpha = o.alpha_last;
+    if (rr_new) *rr_new = o.rr[1];
+    if (beta) *beta = o.beta_last;
+    return done(check_device_error(h, o));
 }
 
 int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch)

@@ -893,6 +893,9 @@ struct PersistArgs {
     int rows_smem;     // the first rows_smem rows of every CTA's block stay resident in shared memory
     int rows_max;      // max rows per CTA (sizes the task-partial array)
     int ll_copies;     // generation 4: replicas of the gathered-Ap array (CTA c polls replica c % ll_copies)
+    int publish_staged; // generation 4: 1 = one store per thread through shared memory, 0 = the row's owner stores every replica
+    int poll_delay;    // generation 4: cycles between a thread's arrival at the gather and its first poll
+    int poll_backoff;  // generation 4: nanoseconds of sleep after a poll round that found stale entries
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
@@ -1409,6 +1412,43 @@ __device__ __forceinline__ double persist_block_total(double v, double *s_red)
     return s;
 }
 
+// One group of up to 8 rows of the fourth generation's GEMV over this lane's columns (cbase + 64 k + {0, 1}): acc[j] = partial sum of
+// row j.  SMEM: rows in shared memory, else in global memory (L2); FULL: every lane's columns exist.  Straight-line code.
+template <int PL, bool SMEM, bool FULL>
+__device__ __forceinline__ void v4_gemv_group(const double *__restrict__ rowp, int lda, int cbase, int nrows, const double (&preg)[PL], double (&acc)[8])
+{
+    constexpr int K2 = PL / 2;
+    constexpr int RB = PL >= 8 ? 2 : 4; // rows per batch: RB * K2 loads of 16 bytes in flight (register budget)
+    bool cv[K2];
+#pragma unroll
+    for (int k = 0; k < K2; ++k) cv[k] = FULL || cbase + 64 * k < lda;
+#pragma unroll
+    for (int h = 0; h < 8; h += RB) {
+        double2 av[RB][K2];
+#pragma unroll
+        for (int j = 0; j < RB; ++j)
+#pragma unroll
+            for (int k = 0; k < K2; ++k) {
+                const double *src = rowp + (size_t)(h + j) * lda + 64 * k;
+                av[j][k] = make_double2(0.0, 0.0);
+                if (h + j < nrows && cv[k]) {
+                    if (SMEM) av[j][k] = *reinterpret_cast<const double2 *>(src);
+                    else av[j][k] = __ldg(reinterpret_cast<const double2 *>(src));
+                }
+            }
+#pragma unroll
+        for (int j = 0; j < RB; ++j) {
+            double s = 0.0;
+#pragma unroll
+            for (int k = 0; k < K2; ++k) {
+                s = mul_add(av[j][k].x, preg[2 * k], s);
+                s = mul_add(av[j][k].y, preg[2 * k + 1], s);
+            }
+            acc[h + j] = s;
+        }
+    }
+}
+
 template <int PL, int LD>
 __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
 {
@@ -1431,6 +1471,7 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
     const int rcnt = base + (bid < rem ? 1 : 0);
     const int cbase = warp * SEG + 2 * lane; // this lane's columns: cbase + 64 k + {0, 1}
     const int rows_pad = (a.rows_max + 7) & ~7;
+    const bool full_cols = lda == NW * SEG; // every lane's columns lie inside the (padded) matrix
     DevState *st = a.st;
 
     // ---- init: p = r = b in registers (b is zero padded to lda), own x = 0, bb = b.b (same order in every CTA)
@@ -1459,6 +1500,7 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
 
     double rr = bb, beta = 0.0;
     int it;
+    int poll_delay = a.poll_delay; // cycles between arriving at the gather and the first poll (grows when that poll comes too early)
     bool converged = false, broke = false;
     long long ph[6] = {0, 0, 0, 0, 0, 0}; // p update | GEMV | row sums + publish | gather Ap | p.Ap, alpha, r, r.r | beta, stop test
     long long tc = clock64();
@@ -1473,6 +1515,21 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
         // ---- GEMV: 8 rows at a time over this warp's column segment
         for (int g0 = 0; g0 < rcnt; g0 += 8) {
             double acc[8];
+            const int nrows = rcnt - g0 < 8 ? rcnt - g0 : 8;
+            const bool all_smem = g0 + nrows <= nres, all_global = g0 >= nres;
+            if (all_smem || all_global) {
+                // fast paths (every row of the group comes from the same place: shared memory — the n = 2048 layout — or L2):
+                // straight-line code, RB rows x K2 16-byte loads issued before their products; row validity is a warp-uniform
+                // predicate, column validity (only when the matrix is narrower than the 16 warps' segments) a per-lane one.  The
+                // branchy general path below exposed one load latency per row (n = 2048: 3.9 k cycles for 14 rows, 3.35 k here).
+                if (all_smem) {
+                    if (full_cols) v4_gemv_group<PL, true, true>(arows + (size_t)g0 * lda + cbase, lda, cbase, nrows, preg, acc);
+                    else v4_gemv_group<PL, true, false>(arows + (size_t)g0 * lda + cbase, lda, cbase, nrows, preg, acc);
+                } else {
+                    if (full_cols) v4_gemv_group<PL, false, true>(a.A + (size_t)(r0 + g0) * lda + cbase, lda, cbase, nrows, preg, acc);
+                    else v4_gemv_group<PL, false, false>(a.A + (size_t)(r0 + g0) * lda + cbase, lda, cbase, nrows, preg, acc);
+                }
+            } else {
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
                 acc[j] = 0.0;
@@ -1500,6 +1557,7 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
                         }
                     }
                 }
+            }
             }
             // halving butterfly: each kept value is computed by exactly one lane (see the second generation)
             const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
@@ -1535,14 +1593,14 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
             for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, part[w * rows_pad + tid]);
             Ap_own = sum;
         }
-        if (a.ll_copies <= 4) { // the common case (n >= 512): the owner stores its row's two words into every replica itself
+        if (!a.publish_staged) { // the owner stores its row's two words into every replica itself
             if (tid < rcnt) {
                 const unsigned long long bits = (unsigned long long)__double_as_longlong(Ap_own);
                 const unsigned long long w0 = tag | (bits >> 32), w1 = tag | (bits & 0xffffffffull);
                 for (int copy = 0; copy < a.ll_copies; ++copy) st_relaxed_gpu_v2u64(llw + (size_t)copy * rep_words + 2 * (size_t)(r0 + tid), w0, w1);
             }
-        } else { // many replicas of a tiny system: rcnt rows x ll_copies replicas, one store per thread; the values travel through
-                 // part[0 .. rcnt), which is dead by now (each owner has read, and now overwrites, only its own column of warp 0's partials)
+        } else { // rcnt rows x ll_copies replicas, one store per thread; the values travel through part[0 .. rcnt), which is dead
+                 // by now (each owner has read, and now overwrites, only its own column of warp 0's partials)
             if (tid < rcnt) part[tid] = Ap_own;
             __syncthreads();
             for (int e = tid; e < rcnt * a.ll_copies; e += NT) {
@@ -1563,6 +1621,13 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
 #pragma unroll
             for (int k = 0; k < K2; ++k) ok[k] = cbase + 64 * k >= n; // nothing beyond n (n is even or the odd tail is handled below)
             const long long t0 = clock64();
+            // The words need one L2 hop (~800 cycles) after the slowest CTA's store.  Polling earlier only puts 148 x 512 load
+            // requests in front of those stores and costs a whole extra round (n = 1024: 254 k it/s with a first poll after 400
+            // cycles, 349 k after 500; profiles/r02_gen4_delay_sweep.log), so a thread waits before its first poll, and waits
+            // longer from then on whenever that first poll still found a stale entry (slower part, other clocks).
+            if (poll_delay > 0)
+                while (clock64() - t0 < poll_delay) {}
+            bool first_round = true;
             for (;;) {
                 bool all = true;
 #pragma unroll
@@ -1578,6 +1643,9 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
                         all = all && ok[k];
                     }
                 if (all) break;
+                if (first_round && a.poll_delay > 0 && poll_delay < 4000) poll_delay += 64;
+                first_round = false;
+                if (a.poll_backoff > 0) __nanosleep(a.poll_backoff);
                 if (clock64() - t0 > 4000000000LL) {
                     st->error = 3;
                     __threadfence_system();

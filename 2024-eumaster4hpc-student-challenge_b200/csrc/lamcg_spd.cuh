@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) gemm_splitk_reduce_kernel(GemmArgs g, int
 //     v[k] = v[k-3] + v[k-31]  (mod 2^32),      rand() = v[k] >> 1,
 // which is LINEAR: the host jumps ahead with powers of its 31 x 31 companion matrix and hands every thread the 31-word state at
 // the start of its chunk (lamcg.cu: glibc_states); the thread then produces its chunk sequentially.  Bit-identical to the host
-// stream (tests/test_gpu_spd_generator.py compares with the oracle's rand()-based fill).
+// stream (tests/test_gpu_spd_generator.py compares with a rand()-based fill on the host).
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128) glibc_rand_fill_kernel(double *out, long long count, const unsigned int *states, long long chunk)
 {

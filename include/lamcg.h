@@ -173,6 +173,12 @@ int lamcg_save_solution(lamcg_t *h, const char *path);
 /* One GEMV of the solver's own kernel on this rank's block: y_local = A_local * p, and the fused
  * epilogue value sum_i p[row_offset+i]*y_local[i].  Host pointers; p has n entries. */
 int lamcg_gemv(lamcg_t *h, const void *p, void *y_local, double *p_dot_y);
+/* K2 / K3 in isolation (single rank, no system needed; x, r, p, Ap are n-element host arrays of the handle's type, rr = r.r
+ * entering the iteration, pAp = p.Ap): one pass of the vector kernels as they run inside the loop — fused != 0: the cooperative
+ * update_fused_kernel, 0: update_xr_kernel then update_p_kernel.  On return x += alpha p, r -= alpha Ap, p = r + beta p
+ * (OMP.hpp:72-78) and alpha = rr / pAp, rr_new = r.r, beta = rr_new / rr. */
+int lamcg_vector_update_step(lamcg_t *h, size_t n, void *x, void *r, void *p, const void *Ap, double rr, double pAp, int fused,
+                             double *alpha, double *rr_new, double *beta);
 /* Launch the GEMV kernel `reps` times back to back on the solver's stream and return the average
  * device milliseconds per launch (CUDA events on that stream), after `warmup` untimed launches. */
 int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch);

@@ -131,6 +131,31 @@ def test_gemv_generated_matrix_matches_generator(solver, variant):
     assert np.array_equal(y, oracle.gemv(oracle.generate_matrix(n), p))
 
 
+# ------------------------------------------------------------------------- K2 / K3: vector kernels
+@pytest.mark.parametrize("fused", [True, False])
+@pytest.mark.parametrize("n", [1, 2, 31, 256, 257, 1000, 4099, 151553])
+def test_vector_kernels_in_isolation(solver, n, fused):
+    """K2 (x += alpha p, r -= alpha Ap, r.r) and K3 (beta, p = r + beta p) on their own, as one cooperative launch (fused) and as
+    the two kernels NCCL mode uses, against the oracle's axpby / dot (OMP.hpp:233-244, 219-231) on random vectors: the elementwise
+    updates are the same unfused operations in the same order, so x, r and p must agree BIT FOR BIT given the same scalars; r.r
+    is a sum in another order (1e-14 relative).  n = 151553 = 592 CTAs x 256 threads + 1: every CTA of the largest grid and a
+    grid-stride tail."""
+    rng = np.random.default_rng(n)
+    x, r, p, Ap = (rng.standard_normal(n) for _ in range(4))
+    rr = oracle.dot(r, r)
+    pAp = abs(oracle.dot(p, Ap)) + 1.0
+    xg, rg, pg, alpha, rr_new, beta = solver.vector_update_step(x, r, p, Ap, rr, pAp, fused)
+    assert alpha == rr / pAp
+    xo, ro, po = x.copy(), r.copy(), p.copy()
+    oracle.axpby(alpha, p, 1.0, xo)        # x = alpha p + x
+    oracle.axpby(-alpha, Ap, 1.0, ro)      # r = -alpha Ap + r
+    assert np.array_equal(xg, xo) and np.array_equal(rg, ro)
+    assert abs(rr_new - oracle.dot(ro, ro)) <= 1e-14 * oracle.dot(ro, ro)
+    assert beta == rr_new / rr
+    oracle.axpby(1.0, ro, beta, po)        # p = r + beta p
+    assert np.array_equal(pg, po)
+
+
 # ------------------------------------------------------------------------------ generate mode
 def test_generate_mode_golden(solver, golden):
     """Every generate-mode row of tests/golden/golden.json (produced by the unmodified reference)."""

@@ -17,7 +17,9 @@ pytestmark = pytest.mark.gpu
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("n,seed", [(1, 3), (2, 3), (7, 5), (96, 7), (257, 11), (1000, 42)])
+# 1..33: a single CholeskyQR2 panel / the first recursion step around the 32-column leaf; 64, 65, 96: two levels; 257, 1000: the
+# fp64 tensor-core GEMM (results of 64 x 64 and more) with ragged tiles and split-K
+@pytest.mark.parametrize("n,seed", [(1, 3), (2, 3), (7, 5), (31, 2), (32, 4), (33, 6), (64, 8), (65, 9), (96, 7), (257, 11), (1000, 42)])
 def test_generator_matches_numpy_restatement(lamcg, tmp_path, n, seed):
     s = lamcg.Solver(0)
     s.random_spd_system(n, seed)
@@ -38,6 +40,25 @@ def test_generator_matches_numpy_restatement(lamcg, tmp_path, n, seed):
     assert r.converged and parity_util.iterations_within_one_of_reference(r.iterations, A, b, 1000, 1e-9, o.iters)[0]
     assert parity_util.rel_l2(s.solution(), o.x) <= 1e-9
     s.close()
+
+
+@pytest.mark.parametrize("n", [200, 777])
+def test_tensor_core_and_simt_generators_agree(lamcg, tmp_path, n):
+    """The default generator (DMMA products, CholeskyQR2 leaves, device-side glibc stream) against the round-1 algorithm
+    (option spd_simt: SIMT products, recursion to single columns): the same matrix to 1e-12 (both are fp64; only summation
+    orders and the leaf algorithm differ, and the thin QR factor with positive diagonal is unique), bit-identical rhs.  The oracle
+    for both stays the numpy restatement (parity unpinned: the reference needs Intel MKL)."""
+    mats = {}
+    for simt in (0, 1):
+        s = lamcg.Solver(0)
+        s.set_option("spd_simt", simt)
+        s.random_spd_system(n, 13)
+        pa, pb = str(tmp_path / f"A{simt}.bin"), str(tmp_path / f"b{simt}.bin")
+        s.save_system(pa, pb)
+        mats[simt] = (fileformat.read_matrix(pa), fileformat.read_vector(pb))
+        s.close()
+    assert np.array_equal(mats[0][1], mats[1][1])
+    assert np.linalg.norm(mats[0][0] - mats[1][0]) <= 1e-12 * np.linalg.norm(mats[1][0])
 
 
 def test_generator_cli_and_reference_cli_reads_it(tmp_path):
