@@ -495,9 +495,9 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     // persist_variant: 0 auto | 1 first generation (row tasks) | 2 second (p in registers, all rows in shared memory; n <= 4096;
     // auto for n <= 2048) | 3 third (K1's streaming row sweep inside the loop; auto above)
     const bool v2_ok = h->lda <= 4096;
-    // auto: the one-exchange generation wherever p fits the register slices (n <= 4096; measured, profiles/r02_small_n_gen4_final.log:
-    // n = 2048 237 k it/s vs 145 k for the second generation, n = 3000 99 k vs 88 k for the first, n = 4096 39.5 k vs 38.0 k for the third)
-    const bool v4 = v2_ok && (h->opt_persist_variant == 4 || h->opt_persist_variant == 0);
+    // auto: the one-exchange generation below lda = 4096 (measured, profiles/r02_small_n_gen4_final.log: n = 2048 237 k it/s vs 145 k for
+    // the second generation, n = 3000 102 k vs 87 k for the first; at n = 4096 the streaming third generation's 38.1 k beats 36.3 k)
+    const bool v4 = v2_ok && (h->opt_persist_variant == 4 || (h->opt_persist_variant == 0 && h->lda < 4096));
     const bool v2 = v2_ok && h->opt_persist_variant == 2;
     // auto above lda = 2048: up to lda < 4096 the first generation still keeps a useful share of the rows in shared memory
     // (n = 3000: 87.7 k it/s vs 72.9 k for the streaming sweep; equal at 4096), beyond that the sweep wins (n = 8192: 12.2 k vs 9.9 k)

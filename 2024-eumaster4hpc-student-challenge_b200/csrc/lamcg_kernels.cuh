@@ -1413,29 +1413,36 @@ __device__ __forceinline__ double persist_block_total(double v, double *s_red)
 }
 
 // One group of up to 8 rows of the fourth generation's GEMV over this lane's columns (cbase + 64 k + {0, 1}): acc[j] = partial sum of
-// row j.  SMEM: rows in shared memory, else in global memory (L2); FULL: every lane's columns exist.  Straight-line code.
+// row j.  SMEM: rows in shared memory, else in global memory (L2); FULL: every lane's columns exist.  Straight-line code with
+// UNCONDITIONAL loads, so that the RB * K2 loads of a batch are issued back to back (predicated loads were issued one by one: one
+// exposed L2 latency per row at n > 2048): rows beyond nrows re-read the group's last row — their sums land in slots of `part` that
+// nobody reads — and columns beyond lda re-read a valid column, whose product with this lane's p (zero there) is zero.
 template <int PL, bool SMEM, bool FULL>
 __device__ __forceinline__ void v4_gemv_group(const double *__restrict__ rowp, int lda, int cbase, int nrows, const double (&preg)[PL], double (&acc)[8])
 {
     constexpr int K2 = PL / 2;
     constexpr int RB = PL >= 8 ? 2 : 4; // rows per batch: RB * K2 loads of 16 bytes in flight (register budget)
-    bool cv[K2];
+    int coff[K2];
 #pragma unroll
-    for (int k = 0; k < K2; ++k) cv[k] = FULL || cbase + 64 * k < lda;
+    for (int k = 0; k < K2; ++k) coff[k] = (FULL || cbase + 64 * k < lda) ? 64 * k : lda - 2 - cbase;
+    const int lastrow = nrows - 1;
 #pragma unroll
     for (int h = 0; h < 8; h += RB) {
+        if (h > 0 && h >= nrows) { // warp-uniform: nothing left in this group
+#pragma unroll
+            for (int j = 0; j < RB; ++j) acc[h + j] = 0.0;
+            continue;
+        }
         double2 av[RB][K2];
 #pragma unroll
-        for (int j = 0; j < RB; ++j)
+        for (int j = 0; j < RB; ++j) {
+            const double *rp = rowp + (size_t)(h + j < lastrow ? h + j : lastrow) * lda;
 #pragma unroll
             for (int k = 0; k < K2; ++k) {
-                const double *src = rowp + (size_t)(h + j) * lda + 64 * k;
-                av[j][k] = make_double2(0.0, 0.0);
-                if (h + j < nrows && cv[k]) {
-                    if (SMEM) av[j][k] = *reinterpret_cast<const double2 *>(src);
-                    else av[j][k] = __ldg(reinterpret_cast<const double2 *>(src));
-                }
+                if (SMEM) av[j][k] = *reinterpret_cast<const double2 *>(rp + coff[k]);
+                else av[j][k] = __ldg(reinterpret_cast<const double2 *>(rp + coff[k]));
             }
+        }
 #pragma unroll
         for (int j = 0; j < RB; ++j) {
             double s = 0.0;

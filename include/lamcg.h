@@ -90,9 +90,13 @@ const char *lamcg_version(void);
 /* ---- options (all optional; also readable from env LAMCG_<KEY>) ----------------------------- */
 /*  gemv_variant  0 auto | 36 / 32 row sweep, 128-bit loads | 46 / 42 row sweep, 256-bit loads | 11 warp rows + TMA-staged p | 2 TMA ring
  *  loop_mode     0 auto (single rank, fp64, n <= 16384: 3; else 2) | 1 stream | 2 graph | 3 persistent (one cooperative kernel)
- *  persist_variant  0 auto | 1 | 2 | 3: generation of the persistent kernel (rows in shared memory / p in registers / streaming sweep)
- *  persist_cluster  thread-block-cluster size of the persistent kernel's scalar exchange (0 auto, 1 none, 2, 4, 8)
+ *  persist_variant  0 auto | 1 | 2 | 3 | 4: generation of the persistent kernel (rows in shared memory / p in registers / streaming
+ *                sweep / one all-gather of Ap per iteration with redundant scalars; auto: 4 below n = 4081, 3 up to 16384)
+ *  persist_poll_delay (default 700 cycles), persist_ll_copies (1), persist_poll (0), persist_publish (-1 auto): tuning of the
+ *                fourth generation's gather (first-poll delay, replicas, polling load flavour, owner / staged stores)
  *  persist_grid  upper bound on the CTAs of the persistent kernel (0: one per SM)
+ *  fuse_updates  1 (default): K2 + K3 as one cooperative launch (single rank / peer mode); 0: two launches
+ *  spd_simt      1: the SPD generator as in round 1 (SIMT products, recursion to single columns); 0 (default): DMMA + CholeskyQR2 leaves
  *  chunk_iters   iterations per graph launch          time_gemv   0/1 event-time every GEMV (stream mode)
  *  ingest_threads (default 8), ingest_chunk_bytes (default 4 MB): reader threads / staging-chunk size of lamcg_load_matrix
  *  peer_timeout_s (default 600): bound of every in-kernel wait for a peer rank; on expiry the solve returns LAMCG_ERR_DEVICE

@@ -18,7 +18,7 @@ import subprocess
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(REPO, "2024-eumaster4hpc-student-challenge_b200", "liblamcg.so")
-INSN = re.compile(r"/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)")
+INSN = re.compile(r"/\*([0-9a-f]{4,})\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Za-z0-9_.]*)")
 
 
 def kernels(lib: str = LIB) -> dict[str, list[tuple[int, str, str]]]:
