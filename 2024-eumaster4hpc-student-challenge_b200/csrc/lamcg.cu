@@ -90,12 +90,10 @@ struct lamcg {
     size_t ingest_pool_bytes = 0;
     int last_ingest_threads = 0;
     long long last_ingest_chunks = 0;
-    long long opt_persist_rows_smem = -1; // -1: as many resident rows as fit; k >= 0: at most k
-    long long opt_persist_variant = 0;    // 0 auto (fourth generation for n <= 2048, first below 4096, third from there) | 1 first | 2 second (n <= 4096) | 3 third | 4 fourth (n <= 4096)
-    long long opt_persist_ll_copies = 0;  // generation 4: replicas of the gathered-Ap array (0 = auto: ~2048 entries in total)
-    long long opt_persist_publish = -1;   // generation 4: -1 auto | 0 owner stores | 1 staged through shared memory
-    long long opt_persist_poll_delay = 700, opt_persist_poll_backoff = 0; // generation 4: cycles before the first poll / ns between poll rounds
-    long long opt_persist_poll = 0;       // generation 4: polling load of the gathered Ap: 0 ld.relaxed.gpu.v4.u64 | 1 ld.relaxed.gpu.v2.u64 x2 | 2 ld.cg.v2.u64 x2
+    long long opt_persist_rows_smem = -1; // v4: -1: as many resident rows as fit; k >= 0: at most k
+    long long opt_persist_variant = 0;    // 0 auto (v4 below lda = 4096, v3 from there) | 3 | 4 (n <= 4096)
+    long long opt_persist_l2_keep_mb = 64; // generation 3: megabytes of A loaded evict-last (kept in L2 between iterations)
+    long long opt_persist_poll_delay = 700; // v4: cycles before a thread's first poll of the gathered Ap
 
     // comm
     int comm_mode = kCommNone;
@@ -473,11 +471,8 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
 
     int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
     if (h->opt_persist_grid > 0) grid = (int)std::min<long long>(grid, h->opt_persist_grid);
-    // generations 1-3: [2][G][G][kLLStride] tagged scalar words; generation 4: [2][lda][2] tagged entries of the gathered Ap
-    // replicas of the gathered vector (option persist_ll_copies; they only helped while the polls started too early)
-    int ll_copies = 1; // with the delayed first poll one replica is best at every size (profiles/r02_gen4_delay_sweep.log)
-    if (h->opt_persist_ll_copies > 0) ll_copies = (int)std::min<long long>(h->opt_persist_ll_copies, 64);
-    const size_t ll_words = std::max((size_t)2 * kLLStride * grid * grid, (size_t)4 * h->lda * ll_copies);
+    // v3: [2][G][G][kLLStride] tagged scalar words; v4: [2][lda][2] tagged entries of the gathered Ap
+    const size_t ll_words = std::max((size_t)2 * kLLStride * grid * grid, (size_t)4 * h->lda);
     if (!h->persist_ll || h->persist_ll_words < ll_words) {
         cudaFree(h->persist_ll);
         h->persist_ll = nullptr;
@@ -485,59 +480,39 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
         h->persist_ll_words = ll_words;
     }
     const int rows_max = (int)((h->n + grid - 1) / grid);
-    // every generation of the kernel handles one owned row per thread (x, r, Ap of row r0 + tid): a device that offers few SMs
-    // (MIG slice, MPS limit) cannot run n near 16384 in one kernel -> the caller takes the graph loop instead
+    // both kernels handle one owned row per thread (x, r, Ap of row r0 + tid): a device that offers few SMs (MIG slice, MPS limit)
+    // cannot run n near 16384 in one kernel -> the caller takes the graph loop instead
     if (rows_max > kPersistThreads) {
         h->fail(LAMCG_ERR_INVALID, "the one-kernel CG loop needs ceil(n / CTAs) <= %d rows per CTA (n = %zu on %d CTAs gives %d)", kPersistThreads, h->n, grid, rows_max);
         return kPersistUnavailable;
     }
     int dev_smem_max = 0;
     CK(cudaDeviceGetAttribute(&dev_smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, h->device));
-    // persist_variant: 0 auto | 1 first generation (row tasks) | 2 second (p in registers, all rows in shared memory; n <= 4096;
-    // auto for n <= 2048) | 3 third (K1's streaming row sweep inside the loop; auto above)
-    const bool v2_ok = h->lda <= 4096;
-    // auto: the one-exchange generation below lda = 4096 (measured, profiles/r02_small_n_gen4_final.log: n = 2048 237 k it/s vs 145 k for
-    // the second generation, n = 3000 102 k vs 87 k for the first; at n = 4096 the streaming third generation's 38.1 k beats 36.3 k)
-    const bool v4 = v2_ok && (h->opt_persist_variant == 4 || (h->opt_persist_variant == 0 && h->lda < 4096));
-    const bool v2 = v2_ok && h->opt_persist_variant == 2;
-    // auto above lda = 2048: up to lda < 4096 the first generation still keeps a useful share of the rows in shared memory
-    // (n = 3000: 87.7 k it/s vs 72.9 k for the streaming sweep; equal at 4096), beyond that the sweep wins (n = 8192: 12.2 k vs 9.9 k)
-    const bool v3 = !v2 && !v4 && (h->opt_persist_variant == 3 || (h->opt_persist_variant == 0 && h->lda >= 4096));
-    if ((h->opt_persist_variant == 2 || h->opt_persist_variant == 4) && !v2_ok) return h->fail(LAMCG_ERR_INVALID, "persist_variant 2 and 4 need n <= 4096");
-    if (h->opt_persist_variant < 0 || h->opt_persist_variant > 4) return h->fail(LAMCG_ERR_INVALID, "persist_variant must be 0..4");
-    if (h->opt_persist_poll < 0 || h->opt_persist_poll > 2) return h->fail(LAMCG_ERR_INVALID, "persist_poll must be 0..2");
-    const void *kernel = (const void *)cg_persistent_kernel;
-    int segs = 1;
+    // persist_variant: 0 auto | 3 streaming sweep inside the loop (auto from lda = 4096) | 4 one exchange per iteration, p in
+    // registers (n <= 4096; auto below lda = 4096).  Measured (profiles/r02_small_n_gen4_final.log, r02_gen3_l2keep_sweep.log):
+    // n = 2048 237 k it/s (round 1's second generation: 145 k), n = 3000 102 k (first generation: 87 k); at n = 4096 the sweep's
+    // 45 k beats 36 k.
+    if (h->opt_persist_variant != 0 && h->opt_persist_variant != 3 && h->opt_persist_variant != 4)
+        return h->fail(LAMCG_ERR_INVALID, "persist_variant must be 0 (auto), 3 or 4");
+    if (h->opt_persist_variant == 4 && h->lda > 4096) return h->fail(LAMCG_ERR_INVALID, "persist_variant 4 needs n <= 4096");
+    const bool v4 = h->opt_persist_variant == 4 || (h->opt_persist_variant == 0 && h->lda < 4096);
+    const void *kernel;
     size_t fixed;
-    bool resident_rows = true;
     if (v4) {
-        const int pl = h->lda <= 1024 ? 0 : h->lda <= 2048 ? 1 : 2;
-        static const void *const table[3][3] = {
-            {(const void *)cg_persistent_v4_kernel<2, 0>, (const void *)cg_persistent_v4_kernel<2, 1>, (const void *)cg_persistent_v4_kernel<2, 2>},
-            {(const void *)cg_persistent_v4_kernel<4, 0>, (const void *)cg_persistent_v4_kernel<4, 1>, (const void *)cg_persistent_v4_kernel<4, 2>},
-            {(const void *)cg_persistent_v4_kernel<8, 0>, (const void *)cg_persistent_v4_kernel<8, 1>, (const void *)cg_persistent_v4_kernel<8, 2>}};
-        kernel = table[pl][h->opt_persist_poll];
+        kernel = h->lda <= 1024 ? (const void *)cg_persistent_v4_kernel<2> : h->lda <= 2048 ? (const void *)cg_persistent_v4_kernel<4>
+                                                                                           : (const void *)cg_persistent_v4_kernel<8>;
         const size_t rows_pad = ((size_t)rows_max + 7) & ~(size_t)7;
         fixed = rows_pad * (kPersistThreads / 32) * sizeof(double); // per-warp row partials
-    } else if (v2) {
-        kernel = h->lda <= 1024 ? (const void *)cg_persistent_v2_kernel<2> : h->lda <= 2048 ? (const void *)cg_persistent_v2_kernel<4>
-                                                                                           : (const void *)cg_persistent_v2_kernel<8>;
-        const size_t rows_pad = ((size_t)rows_max + 7) & ~(size_t)7;
-        fixed = std::max(rows_pad * (kPersistThreads / 32), (size_t)grid) * sizeof(double); // row partials, reused as the gather buffer
-    } else if (v3) {
+    } else {
         kernel = (const void *)cg_persistent_v3_kernel<8, 2>;
         fixed = (h->lda + (((size_t)rows_max + 7) & ~(size_t)7)) * sizeof(double); // p | Ap of the CTA's rows
-        resident_rows = false;
-    } else {
-        while (segs * 2 * rows_max <= kPersistThreads / 32 && (size_t)(segs * 2) * 64 <= h->lda) segs *= 2;
-        fixed = (h->lda + (((size_t)rows_max * segs + 1) & ~(size_t)1)) * sizeof(double);
     }
     cudaFuncAttributes fattr;
     CK(cudaFuncGetAttributes(&fattr, kernel));
     const size_t stat = fattr.sharedSizeBytes; // static shared memory counts against the same per-block limit
     const size_t budget = (size_t)dev_smem_max > fixed + stat ? (size_t)dev_smem_max - fixed - stat : 0;
-    int rows_smem = resident_rows ? (int)std::min<size_t>((size_t)rows_max, budget / (h->lda * sizeof(double))) : 0;
-    if (v4 && rows_smem < rows_max && rows_smem > 8) rows_smem &= ~7; // whole 8-row groups from one place: the straight-line GEMV path
+    int rows_smem = v4 ? (int)std::min<size_t>((size_t)rows_max, budget / (h->lda * sizeof(double))) : 0;
+    if (rows_smem < rows_max && rows_smem > 8) rows_smem &= ~7; // whole 8-row groups from one place: the straight-line GEMV path
     if (h->opt_persist_rows_smem >= 0) rows_smem = std::min(rows_smem, (int)h->opt_persist_rows_smem);
     const size_t smem = fixed + (size_t)rows_smem * h->lda * sizeof(double);
     CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -558,13 +533,14 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
     a.eps = rel_error;
     a.max_iters = max_iters;
     a.hist_cap = h->opt_history ? h->hist_cap : 0;
-    a.segs = segs;
     a.rows_smem = rows_smem;
     a.rows_max = rows_max;
-    a.ll_copies = ll_copies;
-    a.publish_staged = h->opt_persist_publish >= 0 ? (int)(h->opt_persist_publish != 0) : (ll_copies > 4);
     a.poll_delay = (int)std::max<long long>(0, std::min<long long>(h->opt_persist_poll_delay, 100000));
-    a.poll_backoff = (int)std::max<long long>(0, std::min<long long>(h->opt_persist_poll_backoff, 100000));
+    {   // v3: rows per CTA to keep in L2 between iterations (option persist_l2_keep_mb; measured, profiles/r02_gen3_l2keep_sweep.log:
+        // n = 4096 42.6 -> 45.1 k it/s, 5000 26.2 -> 28.0 k, 8192 12.6 -> 12.8 k, 10000 8.39 -> 8.53 k with 64 MB; more than ~90 MB loses)
+        const size_t keep_bytes = (size_t)std::max<long long>(0, std::min<long long>(h->opt_persist_l2_keep_mb, 120)) << 20;
+        a.rows_l2keep = (int)(keep_bytes / std::max<size_t>(1, (size_t)grid * h->lda * sizeof(double)));
+    }
     void *params[] = {&a};
     // The first cooperative launch of a kernel spends tens of milliseconds in the driver (module load, cooperative-launch setup).
     // Taken once per kernel OUTSIDE the timed region with a zero-iteration launch, so that solve_seconds of a first solve is
@@ -866,7 +842,6 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_gemv_ctas_per_sm = env_ll("gemv_ctas_per_sm", 0);
     h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
     h->opt_persist_variant = env_ll("persist_variant", 0);
-    h->opt_persist_poll = env_ll("persist_poll", 0);
     h->opt_persist_poll_delay = env_ll("persist_poll_delay", 700);
     h->opt_fuse_updates = env_ll("fuse_updates", 1);
     h->opt_ingest_threads = env_ll("ingest_threads", 8);
@@ -932,11 +907,8 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "gemv_ctas_per_sm") h->opt_gemv_ctas_per_sm = value;
     else if (k == "persist_rows_smem") h->opt_persist_rows_smem = value;
     else if (k == "persist_variant") h->opt_persist_variant = value;
-    else if (k == "persist_poll") h->opt_persist_poll = value;
-    else if (k == "persist_ll_copies") h->opt_persist_ll_copies = value;
-    else if (k == "persist_publish") h->opt_persist_publish = value;
+    else if (k == "persist_l2_keep_mb") h->opt_persist_l2_keep_mb = value;
     else if (k == "persist_poll_delay") h->opt_persist_poll_delay = value;
-    else if (k == "persist_poll_backoff") h->opt_persist_poll_backoff = value;
     else if (k == "ingest_threads") h->opt_ingest_threads = value;
     else if (k == "ingest_chunk_bytes") h->opt_ingest_chunk_bytes = value;
     else if (k == "peer_timeout_s") { h->opt_peer_timeout_s = value; h->pv.timeout_cycles = peer_timeout_cycles(h); }

@@ -662,7 +662,7 @@ __global__ void __launch_bounds__(256) update_p_kernel(VecArgs v)
 // because every CTA spins on a value that the last CTA of the same grid produces, so all of them must be resident.
 // =============================================================================================
 template <typename T>
-__global__ void __launch_bounds__(256) update_fused_kernel(VecArgs v)
+__global__ void __launch_bounds__(256, 4) update_fused_kernel(VecArgs v) // 4 CTAs per SM must fit: vec_grid() relies on it
 {
     __shared__ double scratch[32];
     __shared__ double s_scalar;
@@ -866,17 +866,16 @@ __global__ void __launch_bounds__(kStreamThreads) stream_read_kernel(const doubl
 }
 
 // =============================================================================================
-// Persistent single-kernel CG for the latency-bound regime (BASELINE config 5: n = 2048, A = 33.5 MB
-// lives in the 126 MB L2).  One cooperative launch runs the WHOLE solve: an iteration is two
-// grid-wide barriers instead of three kernel launches, the direction vector p never leaves shared
-// memory (every CTA keeps a full copy and recomputes p = r + beta p redundantly from the r slices the
-// other CTAs publish), and alpha/beta are recomputed by every CTA from the same partials in the same
-// order, so all CTAs take the same branch at the stop test.
-//   per iteration:  [p update in smem] -> GEMV of the CTA's rows (row segments spread over 32 warps)
-//                   -> partial p.Ap -> ALL-GATHER+SUM (flags) -> alpha; x,r of own rows; publish r; partial r.r
-//                   -> ALL-GATHER+SUM (flags) -> beta, stop test
-// Same arithmetic as K1/K2/K3 (unfused multiply-add, fixed summation order); same reference loop
-// (OMP.hpp:49-91).
+// Persistent single-kernel CG (single rank, n <= 16384): ONE cooperative launch runs the WHOLE solve — no launches, no ramp-up
+// and tail per GEMV, scalars never leave the SMs.  Two kernels, chosen by size (lamcg.cu: solve_persistent):
+//   * cg_persistent_v4_kernel  (n < 4081)          p in registers, the CTA's rows of A in shared memory, ONE exchange per iteration
+//                                                  (all-gather of Ap as tagged words), dots and scalars computed redundantly;
+//   * cg_persistent_v3_kernel  (up to n = 16384)   K1's streaming row sweep inside the loop, p in shared memory, two scalar
+//                                                  all-reduces + published r per iteration (grid_allgather_sum).
+// The first and second generation (round 1: p in shared memory with row tasks; p in registers with two scalar exchanges — 128 k and
+// 145 k it/s at n = 2048 against 237 k now) were measured against these and removed; their logs are profiles/r01_persist_gen2.log,
+// r01_small_n_*.log and profiles/r02_small_n_gen4*.log.
+// Same arithmetic as K1/K2/K3 (unfused multiply-add, fixed summation orders); same reference loop (OMP.hpp:49-91).
 // =============================================================================================
 struct PersistArgs {
     const double *A;   // [n][lda]
@@ -884,18 +883,16 @@ struct PersistArgs {
     double *x;         // [n] out
     double *r;         // [n] exchange buffer for the r slices
     double *hist;      // nullable
-    unsigned long long *ll;      // [2][grid dst][grid src][2] tagged partial words (p.Ap inboxes, then r.r), zeroed by the host
+    unsigned long long *ll;      // v3: [2][grid dst][grid src][16] tagged partial words (p.Ap inboxes, then r.r); v4: [2][lda][2] tagged
+                                 // entries of the gathered Ap; zeroed by the host
     DevState *st;
     long long n, lda;
     double eps;
     int max_iters, hist_cap;
-    int segs;          // column segments per row (rows*segs tasks are dealt to the warps)
-    int rows_smem;     // the first rows_smem rows of every CTA's block stay resident in shared memory
-    int rows_max;      // max rows per CTA (sizes the task-partial array)
-    int ll_copies;     // generation 4: replicas of the gathered-Ap array (CTA c polls replica c % ll_copies)
-    int publish_staged; // generation 4: 1 = one store per thread through shared memory, 0 = the row's owner stores every replica
-    int poll_delay;    // generation 4: cycles between a thread's arrival at the gather and its first poll
-    int poll_backoff;  // generation 4: nanoseconds of sleep after a poll round that found stale entries
+    int rows_smem;     // v4: the first rows_smem rows of every CTA's block stay resident in shared memory
+    int rows_max;      // max rows per CTA (sizes the row-partial arrays)
+    int rows_l2keep;   // v3: leading rows of every CTA loaded with the L2 evict-last policy (kept in L2 between iterations)
+    int poll_delay;    // v4: cycles between a thread's arrival at the gather and its first poll
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu_u64(const unsigned long long *p)
@@ -1022,355 +1019,6 @@ __device__ __forceinline__ double grid_allgather_sum(double my_partial_t0, unsig
 
 constexpr int kPersistThreads = 512; // 128 registers per thread: the exchange and the GEMV stay spill-free
 
-__global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_kernel(PersistArgs a)
-{
-    // n <= 16384 in this kernel, so every index fits 32 bits (keeps the 64-register budget spill-free)
-    extern __shared__ __align__(16) double psm[];
-    const int n = (int)a.n, lda = (int)a.lda, S = a.segs;
-    double *p = psm;                                  // [lda]
-    double *part = psm + lda;                         // [rows_max * segs] task partial sums
-    double *arows = part + ((a.rows_max * S + 1) & ~1); // [rows_smem][lda] resident rows of A
-    __shared__ double scratch[32];
-    __shared__ double s_bcast;
-    __shared__ double s_gather[kPersistMaxGrid];
-    __shared__ double s_scal[4]; // alpha | beta | rr | converged, computed once per CTA by thread 0
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int nwarps = kPersistThreads / 32;
-    const int G = gridDim.x, bid = blockIdx.x;
-    const int base = n / G, rem = n % G;
-    const int r0 = bid * base + (bid < rem ? bid : rem);
-    const int rcnt = base + (bid < rem ? 1 : 0);
-    const int seglen = ((lda + S - 1) / S + 1) & ~1; // even, so 16-byte loads stay aligned
-    DevState *st = a.st;
-
-    // ---- init: p = b (every CTA), own x = 0, own r = b, bb = b.b (same order in every CTA)
-    double local = 0.0;
-    for (int i = tid; i < lda; i += kPersistThreads) {
-        const double bi = a.b[i];
-        p[i] = bi;
-        local = mul_add(bi, bi, local);
-    }
-    const double bb_t0 = block_sum(local, scratch);
-    if (tid == 0) s_bcast = bb_t0;
-    __syncthreads();
-    const double bb = s_bcast;
-    double x_own = 0.0, r_own = 0.0, Ap_own = 0.0;
-    if (tid < rcnt) r_own = a.b[r0 + tid];
-    // A is constant over the solve: park as many of this CTA's rows as fit in shared memory once, so an
-    // iteration re-reads only the remaining rows from L2 (n = 2048: 13 of the 13-14 rows per CTA are resident)
-    const int nres = rcnt < a.rows_smem ? rcnt : a.rows_smem;
-    {
-        const double *src = a.A + (size_t)r0 * lda;
-        for (int i = 2 * tid; i < nres * lda; i += 2 * kPersistThreads)
-            *reinterpret_cast<double2 *>(arows + i) = __ldg(reinterpret_cast<const double2 *>(src + i));
-    }
-    __syncthreads();
-
-    double rr = bb, beta = 0.0;
-    int it;
-    bool converged = false, broke = false;
-    long long ph[6] = {0, 0, 0, 0, 0, 0}; // phase timers (CTA 0 thread 0 reports): p update, GEMV, row sums, p.Ap exchange, x/r update, r.r exchange
-    long long tc = clock64();
-#define LAMCG_PHASE(k) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; }
-    for (it = 1; it <= a.max_iters; ++it) {
-        if (it > 1) { // p = r + beta p, full vector, from the r slices every CTA published before its r.r partial
-            for (int i = tid; i < n; i += kPersistThreads) p[i] = __dadd_rn(__ldcg(&a.r[i]), __dmul_rn(beta, p[i]));
-            __syncthreads();
-        }
-        LAMCG_PHASE(0)
-        // ---- GEMV of this CTA's rows: task = (row, column segment), one warp per task
-        for (int task = warp; task < rcnt * S; task += nwarps) {
-            const int row = task / S, seg = task - row * S;
-            const int c0 = seg * seglen;
-            const int c1 = c0 + seglen < lda ? c0 + seglen : lda;
-            double acc0 = 0.0, acc1 = 0.0;
-            if (row < nres) {
-                const double *arow = arows + row * lda;
-#pragma unroll 4
-                for (int c = c0 + 2 * lane; c < c1; c += 64) {
-                    const double2 av = *reinterpret_cast<const double2 *>(arow + c);
-                    const double2 pv = *reinterpret_cast<const double2 *>(p + c);
-                    acc0 = mul_add(av.x, pv.x, acc0);
-                    acc1 = mul_add(av.y, pv.y, acc1);
-                }
-            } else {
-                const double *arow = a.A + (size_t)(r0 + row) * lda;
-#pragma unroll 8
-                for (int c = c0 + 2 * lane; c < c1; c += 64) {
-                    const double2 av = __ldg(reinterpret_cast<const double2 *>(arow + c));
-                    const double2 pv = *reinterpret_cast<const double2 *>(p + c);
-                    acc0 = mul_add(av.x, pv.x, acc0);
-                    acc1 = mul_add(av.y, pv.y, acc1);
-                }
-            }
-            const double t = warp_sum(__dadd_rn(acc0, acc1));
-            if (lane == 0) part[task] = t;
-        }
-        __syncthreads();
-        LAMCG_PHASE(1)
-        double contrib = 0.0;
-        if (tid < rcnt) {
-            double sum = 0.0;
-            for (int q = 0; q < S; ++q) sum = __dadd_rn(sum, part[tid * S + q]);
-            Ap_own = sum;
-            contrib = __dmul_rn(p[r0 + tid], sum);
-        }
-        {
-            // with <= 32 rows per CTA the partial lives in warp 0: one shuffle reduction, no CTA barrier
-            const double cta_pap = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
-            const double pAp_w0 = grid_allgather_sum<false>(cta_pap, a.ll, (unsigned int)it, s_gather, &s_bcast, &st->error);
-            if (tid == 0) s_scal[0] = rr / pAp_w0; // alpha = rr / (p.Ap)
-        }
-        LAMCG_PHASE(2)
-        __syncthreads();
-        const double alpha = s_scal[0];
-        LAMCG_PHASE(3)
-        contrib = 0.0;
-        if (tid < rcnt) {
-            x_own = __dadd_rn(__dmul_rn(alpha, p[r0 + tid]), x_own);
-            r_own = __dadd_rn(__dmul_rn(-alpha, Ap_own), r_own);
-            __stcg(&a.r[r0 + tid], r_own);
-            contrib = __dmul_rn(r_own, r_own);
-        }
-        const double cta_rr = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
-        const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)kLLStride * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
-        LAMCG_PHASE(4)
-        if (tid == 0) {
-            const double rel0 = sqrt(rrn_w0 / bb);
-            s_scal[1] = rrn_w0 / rr; // beta = rr_new / rr
-            s_scal[2] = rrn_w0;
-            const bool broke0 = !(rel0 == rel0) || isinf(rel0) || !(s_scal[1] == s_scal[1]);
-            s_scal[3] = rel0 < a.eps ? 1.0 : (broke0 ? 2.0 : 0.0);
-            if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
-        }
-        __syncthreads();
-        beta = s_scal[1];
-        rr = s_scal[2];
-        LAMCG_PHASE(5)
-        if (s_scal[3] == 1.0) { converged = true; break; }
-        if (s_scal[3] == 2.0) { broke = true; break; }
-    }
-    if (tid < rcnt) a.x[r0 + tid] = x_own;
-    if (bid == 0 && tid == 0) {
-        st->bb = bb;
-        st->rr_final = rr;
-        st->iters_done = (converged || broke) ? it : (a.max_iters > 0 ? a.max_iters : 0);
-        st->converged = converged ? 1 : 0;
-        st->breakdown = broke ? 1 : 0;
-        st->max_iters = a.max_iters;
-        st->eps = a.eps;
-        st->done = 1;
-        for (int k = 0; k < 6; ++k) st->phase_cycles[k] = ph[k];
-
-    }
-#undef LAMCG_PHASE
-}
-
-// =============================================================================================
-// Persistent loop, second generation ("column segments", n <= 4096).  Same protocol as cg_persistent_kernel (two
-// tagged-word all-gathers per iteration, redundant scalars), different GEMV and no p in shared memory:
-//   * warp w owns the column segment [w*32*PL, (w+1)*32*PL) of EVERY row of the CTA and keeps its slice of p in
-//     REGISTERS (PL doubles per lane) for the whole solve: p = r + beta p is a register update fed by one coalesced
-//     read of the published r, and a row of A costs one pass over shared memory instead of two (the first
-//     generation re-read p from shared memory for every row: A and p traffic were equal, and the GEMV was
-//     shared-memory-bandwidth bound at 2.2 us for n = 2048);
-//   * the 16 KB that p occupied now hold one more row of A: at n = 2048 all 13-14 rows of a CTA are resident (the
-//     first generation streamed the 14th row from L2 through a single warp, a ~1.5 us critical path);
-//   * 8 rows are accumulated at once and reduced across the warp by a halving butterfly (9 fp64 shuffles per 8
-//     rows instead of 40), the 16 per-warp partials of a row are added in warp order by the row's owner thread.
-// Every sum has a fixed order, so runs are bit-reproducible; arithmetic is the same unfused multiply-add.
-// =============================================================================================
-template <int PL>
-__global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(PersistArgs a)
-{
-    extern __shared__ __align__(16) double psm[];
-    constexpr int NW = kPersistThreads / 32; // 16 warps
-    constexpr int K2 = PL / 2;               // 16-byte loads per lane and row
-    constexpr int SEG = 32 * PL;             // columns per warp
-    constexpr unsigned FULL = 0xffffffffu;
-    const int n = (int)a.n, lda = (int)a.lda;
-    double *arows = psm;                              // [rows_smem][lda] resident rows of A
-    double *part = psm + (size_t)a.rows_smem * lda;   // [NW][rows_max rounded up to 8] per-warp row partials (row index fastest: the
-                                                      // owner threads read consecutive words; [row][warp] cost 13 % bank conflicts, ncu) ...
-    double *s_gather = part;                          // ... reused as the all-gather landing zone [G] (disjoint in time)
-    __shared__ double scratch[32];
-    __shared__ double s_bcast;
-    __shared__ double s_scal[4]; // alpha | beta | rr | stop code, computed once per CTA by thread 0
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int G = gridDim.x, bid = blockIdx.x;
-    const int base = n / G, rem = n % G;
-    const int r0 = bid * base + (bid < rem ? bid : rem);
-    const int rcnt = base + (bid < rem ? 1 : 0);
-    const int cbase = warp * SEG + 2 * lane; // this lane's columns: cbase + 64 k + {0, 1}
-    const int rows_pad = (a.rows_max + 7) & ~7;
-    DevState *st = a.st;
-
-    // ---- init: p = b in registers (b is zero padded to lda), own x = 0, own r = p = b, bb = b.b (same order in every CTA)
-    double preg[PL];
-    double local = 0.0;
-#pragma unroll
-    for (int k = 0; k < K2; ++k) {
-        const int c = cbase + 64 * k;
-        double2 bv = make_double2(0.0, 0.0);
-        if (c < lda) bv = *reinterpret_cast<const double2 *>(a.b + c);
-        preg[2 * k] = bv.x;
-        preg[2 * k + 1] = bv.y;
-        local = mul_add(bv.x, bv.x, local);
-        local = mul_add(bv.y, bv.y, local);
-    }
-    const double bb_t0 = block_sum(local, scratch);
-    if (tid == 0) s_bcast = bb_t0;
-    __syncthreads();
-    const double bb = s_bcast;
-    double x_own = 0.0, r_own = 0.0, p_own = 0.0, Ap_own = 0.0;
-    if (tid < rcnt) r_own = p_own = a.b[r0 + tid];
-    const int nres = rcnt < a.rows_smem ? rcnt : a.rows_smem;
-    {
-        const double *src = a.A + (size_t)r0 * lda;
-        for (int i = 2 * tid; i < nres * lda; i += 2 * kPersistThreads)
-            *reinterpret_cast<double2 *>(arows + i) = __ldg(reinterpret_cast<const double2 *>(src + i));
-    }
-    __syncthreads();
-
-    double rr = bb, beta = 0.0;
-    double2 rnext[K2];
-#pragma unroll
-    for (int k = 0; k < K2; ++k) rnext[k] = make_double2(0.0, 0.0);
-    int it;
-    bool converged = false, broke = false;
-    long long ph[6] = {0, 0, 0, 0, 0, 0};
-    long long tc = clock64();
-#define LAMCG_PHASE(k) { const long long now_ = clock64(); ph[k] += now_ - tc; tc = now_; }
-    for (it = 1; it <= a.max_iters; ++it) {
-        if (it > 1) { // p = r + beta p: register slice from the prefetched r (see the end of the loop body); own rows from r_own
-#pragma unroll
-            for (int k = 0; k < K2; ++k) {
-                const int c = cbase + 64 * k;
-                if (c < n) preg[2 * k] = __dadd_rn(rnext[k].x, __dmul_rn(beta, preg[2 * k]));
-                if (c + 1 < n) preg[2 * k + 1] = __dadd_rn(rnext[k].y, __dmul_rn(beta, preg[2 * k + 1]));
-            }
-            if (tid < rcnt) p_own = __dadd_rn(r_own, __dmul_rn(beta, p_own));
-        }
-        LAMCG_PHASE(0)
-        // ---- GEMV: 8 rows at a time over this warp's column segment
-        for (int g0 = 0; g0 < rcnt; g0 += 8) {
-            double acc[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                acc[j] = 0.0;
-                const int row = g0 + j;
-                if (row < nres) {
-                    const double *arow = arows + row * lda;
-#pragma unroll
-                    for (int k = 0; k < K2; ++k) {
-                        const int c = cbase + 64 * k;
-                        if (c < lda) {
-                            const double2 av = *reinterpret_cast<const double2 *>(arow + c);
-                            acc[j] = mul_add(av.x, preg[2 * k], acc[j]);
-                            acc[j] = mul_add(av.y, preg[2 * k + 1], acc[j]);
-                        }
-                    }
-                } else if (row < rcnt) {
-                    const double *arow = a.A + (size_t)(r0 + row) * lda;
-#pragma unroll
-                    for (int k = 0; k < K2; ++k) {
-                        const int c = cbase + 64 * k;
-                        if (c < lda) {
-                            const double2 av = __ldg(reinterpret_cast<const double2 *>(arow + c));
-                            acc[j] = mul_add(av.x, preg[2 * k], acc[j]);
-                            acc[j] = mul_add(av.y, preg[2 * k + 1], acc[j]);
-                        }
-                    }
-                }
-            }
-            // halving butterfly: after the xor-16/8/4 steps lane l holds the sum of row j = 4*bit4 + 2*bit3 + bit2 over
-            // its 4-lane group's complement; the xor-2/1 steps finish it.  Each kept value is computed by exactly one lane.
-            const bool b4 = (lane & 16) != 0, b3 = (lane & 8) != 0, b2 = (lane & 4) != 0;
-            double v4[4], v2[2];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const double keep = b4 ? acc[4 + i] : acc[i], send = b4 ? acc[i] : acc[4 + i];
-                v4[i] = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 16));
-            }
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const double keep = b3 ? v4[2 + i] : v4[i], send = b3 ? v4[i] : v4[2 + i];
-                v2[i] = __dadd_rn(keep, __shfl_xor_sync(FULL, send, 8));
-            }
-            double v = __dadd_rn(b2 ? v2[1] : v2[0], __shfl_xor_sync(FULL, b2 ? v2[0] : v2[1], 4));
-            v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 2));
-            v = __dadd_rn(v, __shfl_xor_sync(FULL, v, 1));
-            if ((lane & 3) == 0) part[warp * rows_pad + g0 + (b4 ? 4 : 0) + (b3 ? 2 : 0) + (b2 ? 1 : 0)] = v;
-        }
-        __syncthreads();
-        LAMCG_PHASE(1)
-        double contrib = 0.0;
-        if (tid < rcnt) {
-            double sum = 0.0;
-#pragma unroll
-            for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, part[w * rows_pad + tid]);
-            Ap_own = sum;
-            contrib = __dmul_rn(p_own, sum);
-        }
-        {
-            const double cta_pap = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
-            const double pAp_w0 = grid_allgather_sum<false>(cta_pap, a.ll, (unsigned int)it, s_gather, &s_bcast, &st->error);
-            if (tid == 0) s_scal[0] = rr / pAp_w0; // alpha = rr / (p.Ap)
-        }
-        LAMCG_PHASE(2)
-        __syncthreads();
-        const double alpha = s_scal[0];
-        LAMCG_PHASE(3)
-        contrib = 0.0;
-        if (tid < rcnt) {
-            x_own = __dadd_rn(__dmul_rn(alpha, p_own), x_own);
-            r_own = __dadd_rn(__dmul_rn(-alpha, Ap_own), r_own);
-            __stcg(&a.r[r0 + tid], r_own);
-            contrib = __dmul_rn(r_own, r_own);
-        }
-        const double cta_rr = a.rows_max <= 32 ? (warp == 0 ? warp_sum(contrib) : 0.0) : block_sum(contrib, scratch);
-        const double rrn_w0 = grid_allgather_sum<true>(cta_rr, a.ll + (size_t)kLLStride * G * G, (unsigned int)it, s_gather, &s_bcast, &st->error);
-        LAMCG_PHASE(4)
-        // every CTA's r slice is visible now: start the reads the next p update needs, they do not depend on beta and their L2
-        // round trip overlaps thread 0's division / square root and the broadcast barrier
-#pragma unroll
-        for (int k = 0; k < K2; ++k) {
-            const int c = cbase + 64 * k;
-            if (c + 1 < n) rnext[k] = __ldcg(reinterpret_cast<const double2 *>(a.r + c));
-            else if (c < n) rnext[k].x = __ldcg(a.r + c);
-        }
-        if (tid == 0) {
-            const double rel0 = sqrt(rrn_w0 / bb);
-            s_scal[1] = rrn_w0 / rr; // beta = rr_new / rr
-            s_scal[2] = rrn_w0;
-            const bool broke0 = !(rel0 == rel0) || isinf(rel0) || !(s_scal[1] == s_scal[1]);
-            s_scal[3] = rel0 < a.eps ? 1.0 : (broke0 ? 2.0 : 0.0);
-            if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
-        }
-        __syncthreads();
-        beta = s_scal[1];
-        rr = s_scal[2];
-        LAMCG_PHASE(5)
-        if (s_scal[3] == 1.0) { converged = true; break; }
-        if (s_scal[3] == 2.0) { broke = true; break; }
-    }
-    if (tid < rcnt) a.x[r0 + tid] = x_own;
-    if (bid == 0 && tid == 0) {
-        st->bb = bb;
-        st->rr_final = rr;
-        st->iters_done = (converged || broke) ? it : (a.max_iters > 0 ? a.max_iters : 0);
-        st->converged = converged ? 1 : 0;
-        st->breakdown = broke ? 1 : 0;
-        st->max_iters = a.max_iters;
-        st->eps = a.eps;
-        st->done = 1;
-        for (int k = 0; k < 6; ++k) st->phase_cycles[k] = ph[k];
-    }
-#undef LAMCG_PHASE
-}
-
 // =============================================================================================
 // Persistent loop, fourth generation ("gathered Ap", n <= 4096; default for n <= 2048).  Generations 1-3 follow the textbook
 // distribution of CG: every CTA owns the x, r entries of its rows, so an iteration needs TWO grid-wide scalar all-reduces (p.Ap,
@@ -1387,14 +1035,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v2_kernel(Pe
 //   GEMV as in the second generation: warp w owns a column segment of every row of the CTA, p slice in registers, all rows of
 //   the CTA resident in shared memory (n = 2048: 14 x 16 KB), 8 rows accumulated at once, halving butterfly.
 // =============================================================================================
-template <int LD>
+// Two adjacent tagged entries (columns c, c + 1: 32 bytes) in ONE 256-bit relaxed gpu-scope load (sm_100).  Measured against two
+// 128-bit loads and against weak ld.cg polls (profiles/r02_allgather_bench.log, r02_small_n_gen4_final.log): 2235 vs 2431 / 2422
+// cycles per gather round, 234 k vs 223 k it/s at n = 2048.
 __device__ __forceinline__ void ll_load_pair(const unsigned long long *p, unsigned long long (&w)[4])
 {
-    if (LD == 0) asm volatile("ld.relaxed.gpu.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p) : "memory");
-    if (LD == 1) { asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p) : "memory");
-                   asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2) : "memory"); }
-    if (LD == 2) { asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(w[0]), "=l"(w[1]) : "l"(p) : "memory");
-                   asm volatile("ld.global.cg.v2.u64 {%0, %1}, [%2];" : "=l"(w[2]), "=l"(w[3]) : "l"(p + 2) : "memory"); }
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(w[0]), "=l"(w[1]), "=l"(w[2]), "=l"(w[3]) : "l"(p) : "memory");
 }
 
 // Sum of one value per thread over the CTA in a fixed order (lane butterfly, then the 16 warps in index order); the total is
@@ -1456,7 +1102,7 @@ __device__ __forceinline__ void v4_gemv_group(const double *__restrict__ rowp, i
     }
 }
 
-template <int PL, int LD>
+template <int PL>
 __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
 {
     extern __shared__ __align__(16) double psm[];
@@ -1587,35 +1233,16 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
         __syncthreads();
         LAMCG_PHASE(1)
         // ---- the owner of a row adds its 16 warp partials in warp order and publishes the row's Ap as two tagged words
-        // layout [iteration parity][replica][lda][2 words]: double-buffered by parity (WAR: see below); small systems are
-        // replicated so that the 148 polling CTAs spread over more L2 lines instead of hammering n/8 of them (measured,
-        // profiles/r02_gen4_probe.log: n = 2048 180 k it/s with one replica, 218 k with two; n = 512 201 k -> 240 k with four)
-        const size_t rep_words = 2 * (size_t)lda;
-        unsigned long long *llw = a.ll + (size_t)(it & 1) * a.ll_copies * rep_words;
-        const unsigned long long *ll = llw + (size_t)(bid % a.ll_copies) * rep_words;
+        // layout [iteration parity][lda][2 words]: double-buffered by parity (WAR: see below)
+        unsigned long long *ll = a.ll + (size_t)(it & 1) * 2 * (size_t)lda;
         const unsigned long long tag = (unsigned long long)(unsigned int)it << 32;
         if (tid < rcnt) {
             double sum = 0.0;
 #pragma unroll
             for (int w = 0; w < NW; ++w) sum = __dadd_rn(sum, part[w * rows_pad + tid]);
             Ap_own = sum;
-        }
-        if (!a.publish_staged) { // the owner stores its row's two words into every replica itself
-            if (tid < rcnt) {
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(Ap_own);
-                const unsigned long long w0 = tag | (bits >> 32), w1 = tag | (bits & 0xffffffffull);
-                for (int copy = 0; copy < a.ll_copies; ++copy) st_relaxed_gpu_v2u64(llw + (size_t)copy * rep_words + 2 * (size_t)(r0 + tid), w0, w1);
-            }
-        } else { // rcnt rows x ll_copies replicas, one store per thread; the values travel through part[0 .. rcnt), which is dead
-                 // by now (each owner has read, and now overwrites, only its own column of warp 0's partials)
-            if (tid < rcnt) part[tid] = Ap_own;
-            __syncthreads();
-            for (int e = tid; e < rcnt * a.ll_copies; e += NT) {
-                const int row = e % rcnt, copy = e / rcnt;
-                const unsigned long long bits = (unsigned long long)__double_as_longlong(part[row]);
-                st_relaxed_gpu_v2u64(llw + (size_t)copy * rep_words + 2 * (size_t)(r0 + row), tag | (bits >> 32), tag | (bits & 0xffffffffull));
-            }
-            __syncthreads(); // part is rewritten by the next GEMV
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(sum);
+            st_relaxed_gpu_v2u64(ll + 2 * (size_t)(r0 + tid), tag | (bits >> 32), tag | (bits & 0xffffffffull));
         }
         LAMCG_PHASE(2)
         // ---- all-gather: poll the entries of this thread's columns.  A CTA can run at most one iteration ahead of the slowest
@@ -1631,7 +1258,10 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
             // The words need one L2 hop (~800 cycles) after the slowest CTA's store.  Polling earlier only puts 148 x 512 load
             // requests in front of those stores and costs a whole extra round (n = 1024: 254 k it/s with a first poll after 400
             // cycles, 349 k after 500; profiles/r02_gen4_delay_sweep.log), so a thread waits before its first poll, and waits
-            // longer from then on whenever that first poll still found a stale entry (slower part, other clocks).
+            // longer from then on whenever that first poll still found a stale entry (slower part, other clocks).  Measured and
+            // dropped (profiles/r02_gen4_probe.log, r02_gen4_poll_sweep.log): 2-8 replicas of the gathered array (they only helped
+            // while the polls started too early: 180 -> 218 k it/s at n = 2048, against 237 k with the delay and one copy), stores
+            // staged through shared memory, __nanosleep back-off between rounds (168-180 k).
             if (poll_delay > 0)
                 while (clock64() - t0 < poll_delay) {}
             bool first_round = true;
@@ -1639,7 +1269,7 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
                 bool all = true;
 #pragma unroll
                 for (int k = 0; k < K2; ++k)
-                    if (!ok[k]) ll_load_pair<LD>(ll + 2 * (size_t)(cbase + 64 * k), w[k]);
+                    if (!ok[k]) ll_load_pair(ll + 2 * (size_t)(cbase + 64 * k), w[k]);
 #pragma unroll
                 for (int k = 0; k < K2; ++k)
                     if (!ok[k]) {
@@ -1652,7 +1282,6 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
                 if (all) break;
                 if (first_round && a.poll_delay > 0 && poll_delay < 4000) poll_delay += 64;
                 first_round = false;
-                if (a.poll_backoff > 0) __nanosleep(a.poll_backoff);
                 if (clock64() - t0 > 4000000000LL) {
                     st->error = 3;
                     __threadfence_system();
@@ -1752,7 +1381,12 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v3_kernel(Pe
     DevState *st = a.st;
     // a matrix that fits in L2 should stay there between iterations; a larger one is streamed (evict-first) so that it does
     // not push r and the exchange words out
-    const uint64_t polA = (size_t)n * lda * sizeof(double) <= (size_t)96 << 20 ? l2_policy_evict_normal() : l2_policy_evict_first();
+    // a matrix that fits in L2 stays there between iterations; of a larger one the first rows_l2keep rows of every CTA are loaded
+    // evict-last (together ~80 MB of the 126 MB L2: that slice is served from L2 in every iteration after the first) and the rest is
+    // streamed evict-first so that it does not push that slice, r and the exchange words out
+    const bool fits_l2 = (size_t)n * lda * sizeof(double) <= (size_t)96 << 20;
+    const uint64_t polStream = fits_l2 ? l2_policy_evict_normal() : l2_policy_evict_first();
+    const uint64_t polKeep = fits_l2 ? l2_policy_evict_normal() : l2_policy_evict_last();
 
     double local = 0.0;
     for (int i = tid; i < lda; i += NT) {
@@ -1800,7 +1434,7 @@ __global__ void __launch_bounds__(kPersistThreads, 1) cg_persistent_v3_kernel(Pe
 #pragma unroll
                     for (int u = 0; u < U; ++u) {
                         const int c = c0 + 2 * tid + u * NT * 2;
-                        av[r][u] = (cv[u] && r < nr) ? ldg_stream_f64x2(arow0 + (size_t)r * lda + c, polA) : make_double2(0.0, 0.0);
+                        av[r][u] = (cv[u] && r < nr) ? ldg_stream_f64x2(arow0 + (size_t)r * lda + c, pr + r < a.rows_l2keep ? polKeep : polStream) : make_double2(0.0, 0.0);
                     }
                 }
 #pragma unroll

@@ -90,17 +90,17 @@ const char *lamcg_version(void);
 /* ---- options (all optional; also readable from env LAMCG_<KEY>) ----------------------------- */
 /*  gemv_variant  0 auto | 36 / 32 row sweep, 128-bit loads | 46 / 42 row sweep, 256-bit loads | 11 warp rows + TMA-staged p | 2 TMA ring
  *  loop_mode     0 auto (single rank, fp64, n <= 16384: 3; else 2) | 1 stream | 2 graph | 3 persistent (one cooperative kernel)
- *  persist_variant  0 auto | 1 | 2 | 3 | 4: generation of the persistent kernel (rows in shared memory / p in registers / streaming
- *                sweep / one all-gather of Ap per iteration with redundant scalars; auto: 4 below n = 4081, 3 up to 16384)
- *  persist_poll_delay (default 700 cycles), persist_ll_copies (1), persist_poll (0), persist_publish (-1 auto): tuning of the
- *                fourth generation's gather (first-poll delay, replicas, polling load flavour, owner / staged stores)
+ *  persist_variant  0 auto | 3 | 4: kernel of the one-kernel loop (3: K1's streaming sweep inside the loop, two scalar exchanges,
+ *                auto from n = 4081 to 16384; 4: one all-gather of Ap per iteration with redundant scalars, n <= 4096, auto below)
+ *  persist_poll_delay (default 700 cycles: a thread's first poll of the gathered Ap), persist_l2_keep_mb (default 64: megabytes of A
+ *                the streaming kernel loads with the L2 evict-last policy), persist_rows_smem: tuning of the one-kernel loop
  *  persist_grid  upper bound on the CTAs of the persistent kernel (0: one per SM)
  *  fuse_updates  1 (default): K2 + K3 as one cooperative launch (single rank / peer mode); 0: two launches
  *  spd_simt      1: the SPD generator as in round 1 (SIMT products, recursion to single columns); 0 (default): DMMA + CholeskyQR2 leaves
  *  chunk_iters   iterations per graph launch          time_gemv   0/1 event-time every GEMV (stream mode)
  *  ingest_threads (default 8), ingest_chunk_bytes (default 4 MB): reader threads / staging-chunk size of lamcg_load_matrix
  *  peer_timeout_s (default 600): bound of every in-kernel wait for a peer rank; on expiry the solve returns LAMCG_ERR_DEVICE
- *  gemv_ctas_per_sm, persist_rows_smem  tuning overrides     history  0/1 keep sqrt(rr/bb) per iteration (default 1)
+ *  gemv_ctas_per_sm  tuning override     history  0/1 keep sqrt(rr/bb) per iteration (default 1)
  *  debug_persist_fail  test hook: pretend the cooperative launch of the persistent kernel was refused */
 int lamcg_set_option(lamcg_t *h, const char *key, long long value);
 int lamcg_get_info(const lamcg_t *h, lamcg_info *out);
@@ -186,9 +186,10 @@ int lamcg_vector_update_step(lamcg_t *h, size_t n, void *x, void *r, void *p, co
 /* Launch the GEMV kernel `reps` times back to back on the solver's stream and return the average
  * device milliseconds per launch (CUDA events on that stream), after `warmup` untimed launches. */
 int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch);
-/* Persistent loop only: SM cycles CTA 0 spent in each phase of the last solve, summed over its iterations
- * [0] p update  [1] GEMV  [2] row sums + p.Ap exchange  [3] alpha broadcast  [4] x/r update + r.r exchange
- * [5] beta broadcast.  Returns the count. */
+/* Persistent loop only: SM cycles CTA 0 spent in each phase of the last solve, summed over its iterations.
+ * v3: [0] p update  [1] GEMV  [2] row sums + p.Ap exchange  [3] alpha broadcast  [4] x/r update + r.r exchange  [5] beta broadcast.
+ * v4: [0] p update  [1] GEMV  [2] row sums + publish  [3] gather of Ap  [4] p.Ap, alpha, r, r.r  [5] beta, stop test.
+ * Returns the count. */
 int lamcg_get_loop_profile(lamcg_t *h, long long *cycles_out, int capacity);
 /* Plain streaming read of this rank's block (sum of all elements): the read-only HBM ceiling the
  * GEMV is compared with.  Returns average ms per pass and the checksum. */

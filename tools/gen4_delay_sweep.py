@@ -13,11 +13,9 @@ for n in [int(x) for x in (sys.argv[1:] or ["256", "512", "1024", "2048", "3000"
     s.generate_rhs()
     s.set_option("loop_mode", 3)
     s.set_option("persist_variant", 4)
-    s.set_option("persist_publish", 0)
-    for copies in (1, 2, 4, 8):
+    for copies in (1,):  # replicas of the gathered array were dropped after this sweep (profiles/r02_gen4_delay_sweep.log)
         line = []
         for delay in (0, 200, 400, 500, 600, 700, 800, 1000):
-            s.set_option("persist_ll_copies", copies)
             s.set_option("persist_poll_delay", delay)
             s.solve(iters, 0.0)
             rates = []

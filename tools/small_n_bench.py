@@ -12,14 +12,10 @@ for n in [int(x) for x in (sys.argv[1:] or ["2048"])]:
     s.generate_rhs()
     iters = 2000
     for name, opts in [("graph", {"loop_mode": 2}), ("stream", {"loop_mode": 1}),
-                       ("persistent gen1 rows_smem=0", {"loop_mode": 3, "persist_rows_smem": 0, "persist_variant": 1}),
-                       ("persistent gen1 rows_smem=auto", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 1}),
-                       ("persistent gen2 (p in registers)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 2}),
-                       ("persistent gen3 (streaming sweep)", {"loop_mode": 3, "persist_rows_smem": -1, "persist_variant": 3}),
-                       ("persistent gen4 (gathered Ap) poll v4.u64", {"loop_mode": 3, "persist_variant": 4, "persist_poll": 0}),
-                       ("persistent gen4 (gathered Ap) poll v2.u64 x2", {"loop_mode": 3, "persist_variant": 4, "persist_poll": 1}),
-                       ("persistent gen4 (gathered Ap) poll ld.cg", {"loop_mode": 3, "persist_variant": 4, "persist_poll": 2})]:
-        if n > 4096 and opts.get("persist_variant") in (2, 4):
+                       ("persistent v3 (streaming sweep)", {"loop_mode": 3, "persist_variant": 3}),
+                       ("persistent v4 (gathered Ap)", {"loop_mode": 3, "persist_variant": 4}),
+                       ("persistent auto", {"loop_mode": 3, "persist_variant": 0})]:
+        if n > 4096 and opts.get("persist_variant") == 4:
             continue
         for k, v in opts.items():
             s.set_option(k, v)
