@@ -27,7 +27,7 @@ from . import launch  # noqa: F401  (host-side multi-rank plumbing)
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(HERE)
-LIB_PATH = os.path.join(HERE, "liblamcg.so")
+LIB_PATH = os.environ.get("LAMCG_LIB") or os.path.join(HERE, "liblamcg.so")  # LAMCG_LIB: an alternative build of the same library (A/B measurements)
 HEADER_PATH = os.path.join(REPO, "include", "lamcg.h")
 
 NCCL_ID_BYTES = 128

@@ -93,7 +93,7 @@ struct lamcg {
     long long opt_persist_rows_smem = -1; // v4: -1: as many resident rows as fit; k >= 0: at most k
     long long opt_persist_variant = 0;    // 0 auto (v4 below lda = 4096, v3 from there) | 3 | 4 (n <= 4096)
     long long opt_persist_l2_keep_mb = 64; // generation 3: megabytes of A loaded evict-last (kept in L2 between iterations)
-    long long opt_persist_poll_delay = 700; // v4: cycles before a thread's first poll of the gathered Ap
+    long long opt_persist_poll_delay = 650; // v4: cycles before a thread's first poll of the gathered Ap
 
     // comm
     int comm_mode = kCommNone;
@@ -842,7 +842,7 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_gemv_ctas_per_sm = env_ll("gemv_ctas_per_sm", 0);
     h->opt_persist_rows_smem = env_ll("persist_rows_smem", -1);
     h->opt_persist_variant = env_ll("persist_variant", 0);
-    h->opt_persist_poll_delay = env_ll("persist_poll_delay", 700);
+    h->opt_persist_poll_delay = env_ll("persist_poll_delay", 650);
     h->opt_fuse_updates = env_ll("fuse_updates", 1);
     h->opt_ingest_threads = env_ll("ingest_threads", 8);
     h->opt_ingest_chunk_bytes = env_ll("ingest_chunk_bytes", 4ll << 20);

@@ -1067,10 +1067,38 @@ template <int PL, bool SMEM, bool FULL>
 __device__ __forceinline__ void v4_gemv_group(const double *__restrict__ rowp, int lda, int cbase, int nrows, const double (&preg)[PL], double (&acc)[8])
 {
     constexpr int K2 = PL / 2;
-    constexpr int RB = PL >= 8 ? 2 : 4; // rows per batch: RB * K2 loads of 16 bytes in flight (register budget)
+    constexpr int RB = PL >= 8 ? 2 : 4; // rows per batch: RB * K2 loads of 16 bytes in flight (8 rows per batch measured slower:
+                                        // 3513 vs 3318 cycles for the 14 rows at n = 2048, profiles/r02_gen4_gemv_ab.log)
+    if (FULL) lda = 16 * 32 * PL; // FULL means lda == 16 warps x 32 lanes x PL columns: a compile-time row stride, so the loads of a
+                                  // full group are addressed by immediate offsets (no per-row multiply / clamp instructions)
     int coff[K2];
 #pragma unroll
     for (int k = 0; k < K2; ++k) coff[k] = (FULL || cbase + 64 * k < lda) ? 64 * k : lda - 2 - cbase;
+    if (nrows == 8) { // warp-uniform: the common case, no index clamping
+#pragma unroll
+        for (int h = 0; h < 8; h += RB) {
+            double2 av[RB][K2];
+#pragma unroll
+            for (int j = 0; j < RB; ++j)
+#pragma unroll
+                for (int k = 0; k < K2; ++k) {
+                    const double *src = rowp + (size_t)(h + j) * lda + coff[k];
+                    if (SMEM) av[j][k] = *reinterpret_cast<const double2 *>(src);
+                    else av[j][k] = __ldg(reinterpret_cast<const double2 *>(src));
+                }
+#pragma unroll
+            for (int j = 0; j < RB; ++j) {
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < K2; ++k) {
+                    s = mul_add(av[j][k].x, preg[2 * k], s);
+                    s = mul_add(av[j][k].y, preg[2 * k + 1], s);
+                }
+                acc[h + j] = s;
+            }
+        }
+        return;
+    }
     const int lastrow = nrows - 1;
 #pragma unroll
     for (int h = 0; h < 8; h += RB) {
@@ -1300,8 +1328,17 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
         local = 0.0;
 #pragma unroll
         for (int k = 0; k < PL; ++k) local = mul_add(preg[k], ap[k], local);
-        const double pAp = persist_block_total(local, s_red);
-        if (tid == 0) s_scal[0] = rr / pAp; // alpha = rr / (p.Ap): one division per CTA, broadcast
+        // block total in the fixed order (lane butterfly, then the 16 warps in index order), finished by warp 0 alone, which
+        // also derives the scalar: two CTA barriers per reduction instead of three
+        local = warp_sum(local);
+        if (lane == 0) s_red[warp] = local;
+        __syncthreads();
+        if (warp == 0) {
+            double pAp = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) pAp = __dadd_rn(pAp, s_red[w]);
+            if (lane == 0) s_scal[0] = rr / pAp; // alpha = rr / (p.Ap): one division per CTA, broadcast
+        }
         __syncthreads();
         const double alpha = s_scal[0], nalpha = -alpha;
         local = 0.0;
@@ -1314,15 +1351,22 @@ __global__ void __launch_bounds__(512, 1) cg_persistent_v4_kernel(PersistArgs a)
             x_own = __dadd_rn(__dmul_rn(alpha, p_own), x_own);       // axpby(alpha, p, 1.0, x)
             r_own = __dadd_rn(__dmul_rn(nalpha, Ap_own), r_own);
         }
-        const double rrn = persist_block_total(local, s_red);
+        local = warp_sum(local);
+        if (lane == 0) s_red[warp] = local; // (every thread has read alpha past the barrier above; s_red's readers were warp 0 before it)
+        __syncthreads();
         LAMCG_PHASE(4)
-        if (tid == 0) {
-            const double rel0 = sqrt(rrn / bb);
-            s_scal[1] = rrn / rr; // beta = rr_new / rr
-            s_scal[2] = rrn;
-            const bool broke0 = !(rel0 == rel0) || isinf(rel0) || !(s_scal[1] == s_scal[1]);
-            s_scal[3] = rel0 < a.eps ? 1.0 : (broke0 ? 2.0 : 0.0);
-            if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
+        if (warp == 0) {
+            double rrn = 0.0;
+#pragma unroll
+            for (int w = 0; w < NW; ++w) rrn = __dadd_rn(rrn, s_red[w]);
+            if (lane == 0) {
+                const double rel0 = sqrt(rrn / bb);
+                s_scal[1] = rrn / rr; // beta = rr_new / rr
+                s_scal[2] = rrn;
+                const bool broke0 = !(rel0 == rel0) || isinf(rel0) || !(s_scal[1] == s_scal[1]);
+                s_scal[3] = rel0 < a.eps ? 1.0 : (broke0 ? 2.0 : 0.0);
+                if (bid == 0 && a.hist && it - 1 < a.hist_cap) a.hist[it - 1] = rel0;
+            }
         }
         __syncthreads();
         beta = s_scal[1];

@@ -92,7 +92,7 @@ const char *lamcg_version(void);
  *  loop_mode     0 auto (single rank, fp64, n <= 16384: 3; else 2) | 1 stream | 2 graph | 3 persistent (one cooperative kernel)
  *  persist_variant  0 auto | 3 | 4: kernel of the one-kernel loop (3: K1's streaming sweep inside the loop, two scalar exchanges,
  *                auto from n = 4081 to 16384; 4: one all-gather of Ap per iteration with redundant scalars, n <= 4096, auto below)
- *  persist_poll_delay (default 700 cycles: a thread's first poll of the gathered Ap), persist_l2_keep_mb (default 64: megabytes of A
+ *  persist_poll_delay (default 650 cycles: a thread's first poll of the gathered Ap), persist_l2_keep_mb (default 64: megabytes of A
  *                the streaming kernel loads with the L2 evict-last policy), persist_rows_smem: tuning of the one-kernel loop
  *  persist_grid  upper bound on the CTAs of the persistent kernel (0: one per SM)
  *  fuse_updates  1 (default): K2 + K3 as one cooperative launch (single rank / peer mode); 0: two launches
