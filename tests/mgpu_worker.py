@@ -153,6 +153,38 @@ def main():
         ok = ok and good
         report["cases"].append(entry)
 
+    def case_peer_timeout():
+        """A peer rank that never reaches the exchange (round-1 ADVICE: the 30 s wait ended in __trap(), which poisons the CUDA
+        context of the whole process).  Rank 1 simply does not solve; rank 0's in-kernel wait expires after peer_timeout_s, the
+        solve returns LAMCG_ERR_DEVICE with a message that names the timeout, and the SAME process can go on using the GPU."""
+        nonlocal ok
+        n = 4096
+        s = lamcg_b200.Solver(local, rank, world)
+        lamcg_b200.launch.bootstrap_comm(s, n=n, mode="peer", dist=dist)
+        s.set_option("peer_timeout_s", 2)
+        s.generate_matrix(n, n)
+        s.generate_rhs()
+        dist.barrier()
+        entry = {"name": "peer_timeout", "n": n}
+        if rank == 0:
+            try:
+                s.solve(50, 1e-9)
+                entry["error"] = None
+            except lamcg_b200.LamcgError as e:
+                entry["error"] = [e.code, e.message]
+            good = entry["error"] is not None and entry["error"][0] == -8 and "peer flag timeout" in entry["error"][1]
+            t = lamcg_b200.Solver(local)             # the context survived: a fresh single-rank solve on the same GPU is right
+            t.generate_matrix(1000, 1000)
+            t.generate_rhs()
+            r = t.solve(10000, 1e-9)
+            good = good and bool(r.converged) and r.iterations == 500
+            t.close()
+            entry["ok"] = bool(good)
+            ok = ok and good
+            report["cases"].append(entry)
+        dist.barrier()                               # rank 1 keeps its exchange buffer mapped until rank 0 is done
+        s.close()
+
     import tempfile
     tmpdir = os.environ.get("LAMCG_TEST_TMP") or tempfile.gettempdir()
     case_resume("resume_odd", 10007, 37, 64, 2, tmpdir)       # odd k: one plain step before the graph chunks
@@ -165,6 +197,9 @@ def main():
     case("spd_file", 1024, spd(1024, 11), 1000, 2, 1e-9)  # stops may differ by an iteration: see tests/test_gpu_parity.py X_TOL_STOPPED
     case("gen_big", 40000, gen(40000, 100), 100, 2, 1e-12)
     case("gen_f32", 4100, gen(4100, 120), 120, 2, 1e-4, dtype="f32")  # fp32 storage across ranks (p slices, x gather in floats)
+
+    if comm == "peer" and world == 2:
+        case_peer_timeout()
 
     if rank == 0:
         report["ok"] = bool(ok)
