@@ -83,6 +83,7 @@ struct lamcg {
     long long opt_peer_timeout_s = 600;   // bound of every peer flag wait; ranks may finish a cold-cache ingest minutes apart
     long long opt_persist_grid = 0;       // 0: one CTA per SM; k > 0: at most k CTAs in the one-kernel loop (tests: small-device behaviour)
     long long opt_debug_persist_fail = 0; // test hook: pretend the cooperative launch was refused
+    long long opt_loop_profile = 0;       // multi-rank stream / graph loop: CTA 0 of K1 / K2+K3 accumulates wait and work cycles (lamcg_get_loop_profile)
     long long opt_fuse_updates = 1;       // K2 + K3 in one cooperative launch (single rank / peer mode)
     long long opt_spd_simt = 0;           // 1: the SPD generator's products on the SIMT kernel only (comparison / fallback)
     int clock_khz = 1965000;
@@ -323,6 +324,7 @@ GemvArgs gemv_args(lamcg *h, int check_done, int par)
     g.lda = (long long)h->lda;
     g.row_offset = (long long)h->row_offset;
     g.check_done = check_done;
+    g.prof = h->opt_loop_profile ? 1 : 0;
     return g;
 }
 
@@ -362,6 +364,7 @@ VecArgs vec_args(lamcg *h, int par)
     v.row_offset = (long long)h->row_offset;
     v.par = par;
     v.fused = fuse_updates(h) ? 1 : 0;
+    v.prof = h->opt_loop_profile ? 1 : 0;
     return v;
 }
 
@@ -916,6 +919,7 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "debug_persist_fail") h->opt_debug_persist_fail = value;
     else if (k == "spd_simt") h->opt_spd_simt = value;
     else if (k == "fuse_updates") h->opt_fuse_updates = value;
+    else if (k == "loop_profile") h->opt_loop_profile = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
     if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
     if (h->alloc_n) {
@@ -1800,6 +1804,7 @@ int lamcg_vector_update_step(lamcg_t *h, size_t n, void *x, void *r, void *p, co
     v.row_offset = 0;
     v.par = 0;
     v.fused = fused ? 1 : 0;
+    v.prof = 0;
     const int vg = (int)std::min<size_t>(std::max<size_t>((n + kVecThreads - 1) / kVecThreads, 1), (size_t)h->sm_count * 4); // vec_grid() of an n-row rank
     if (fused) {
         void *params[] = {&v};

@@ -28,6 +28,7 @@ struct GemvArgs {
     long long row_offset; // global index of local row 0 (p is indexed globally)
     int check_done;     // 1 inside the solve loop, 0 for the standalone GEMV hook
     int par;            // iteration parity (scalar double-buffer slot, peer slot / p buffer)
+    int prof;           // 1: CTA 0 adds the SM cycles it waits for the peers' p to st->phase_cycles[0] (option loop_profile)
     PeerView pv;        // pv.nranks <= 1: no peer exchange
 };
 
@@ -41,7 +42,13 @@ __device__ __forceinline__ bool gemv_peer_prologue(const GemvArgs &g, unsigned l
     const int it = g.st->iter[g.par];
     const unsigned long long base = g.st->seq_base;
     seq = base + (unsigned long long)it + 1ull;
-    if (it >= 1) return peer_wait_all(peer_hdr(g.pv, g.pv.me)->p_flag, g.pv.nranks, base + (unsigned long long)it, g.st, g.pv.timeout_cycles);
+    if (it >= 1) {
+        const bool prof = g.prof && blockIdx.x == 0 && threadIdx.x == 0;
+        const long long tc = prof ? clock64() : 0;
+        const bool ok = peer_wait_all(peer_hdr(g.pv, g.pv.me)->p_flag, g.pv.nranks, base + (unsigned long long)it, g.st, g.pv.timeout_cycles);
+        if (prof) g.st->phase_cycles[0] += clock64() - tc; // K1: wait for every rank's slice of p
+        return ok;
+    }
     return true;
 }
 
@@ -505,6 +512,7 @@ struct VecArgs {
     long long rows, row_offset;
     int par;                // iteration parity for the double-buffered scalars
     int fused;              // 1: launched as update_fused_kernel (K2's last CTA also releases st->rrn_ready)
+    int prof;               // 1: CTA 0 adds the SM cycles it spends per phase to st->phase_cycles[2..5] (option loop_profile)
     PeerView pv;            // pv.nranks <= 1: no peer exchange
 };
 
@@ -517,10 +525,13 @@ __device__ __forceinline__ bool xr_phase(const VecArgs &v, double *scratch /* 32
     const T *vAp = static_cast<const T *>(v.Ap);
     unsigned long long seq = 0ull;
     double pAp;
+    const bool prof = v.prof && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tc = prof ? clock64() : 0;
     if (v.pv.nranks > 1) { // peer mode: the all-reduce of p.Ap is a wait on nranks flags + a fixed-order sum
         seq = st->seq_base + (unsigned long long)st->iter[v.par] + 1ull;
         PeerHeader *me = peer_hdr(v.pv, v.pv.me);
         if (!peer_wait_all(me->pap_flag, v.pv.nranks, seq, st, v.pv.timeout_cycles)) return false;
+        if (prof) { const long long now = clock64(); st->phase_cycles[2] += now - tc; tc = now; } // wait for every rank's p.Ap
         if (threadIdx.x == 0) *s_pAp = peer_sum_slots(me->pap_slot[v.par], v.pv.nranks);
         __syncthreads();
         pAp = *s_pAp;
@@ -544,6 +555,7 @@ __device__ __forceinline__ bool xr_phase(const VecArgs &v, double *scratch /* 32
         grid_sum_publish(cta, v.partials, &st->ticket_xr, &st->rrn_local, threadIdx.x, &v.pv, 1, v.par, seq, v.fused ? &st->rrn_ready : nullptr,
                          (unsigned int)(st->iter[v.par] + 1));
     }
+    if (prof) st->phase_cycles[3] += clock64() - tc; // x, r update, r.r partial, publish
     return true;
 }
 
@@ -607,10 +619,13 @@ __device__ __forceinline__ void p_phase(const VecArgs &v, double *s_rrn, int *s_
     DevState *st = v.st;
     const int it0 = st->iter[v.par];
     double rr_new;
+    const bool prof = v.prof && blockIdx.x == 0 && threadIdx.x == 0;
+    long long tc = prof ? clock64() : 0;
     if (v.pv.nranks > 1) {
         const unsigned long long seq = st->seq_base + (unsigned long long)it0 + 1ull;
         PeerHeader *me = peer_hdr(v.pv, v.pv.me);
         if (!peer_wait_all(me->rrn_flag, v.pv.nranks, seq, st, v.pv.timeout_cycles)) return;
+        if (prof) { const long long now = clock64(); st->phase_cycles[4] += now - tc; tc = now; } // wait for every rank's r.r
         if (threadIdx.x == 0) *s_rrn = peer_sum_slots(me->rrn_slot[v.par], v.pv.nranks);
         __syncthreads();
         rr_new = *s_rrn;
@@ -629,6 +644,7 @@ __device__ __forceinline__ void p_phase(const VecArgs &v, double *s_rrn, int *s_
     const bool fin = conv || broke || it >= st->max_iters;
 
     if (!fin) p_update<T>(v, beta, it, s_last);
+    if (prof) st->phase_cycles[5] += clock64() - tc; // beta, stop test, p = r + beta p, peer stores of the slice, fence, flags
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         st->rr[v.par ^ 1] = rr_new;
         st->iter[v.par ^ 1] = it;
@@ -797,6 +813,7 @@ __global__ void __launch_bounds__(1024) init_solve_kernel(InitArgs a)
         st->hist_cap = a.hist_cap;
         st->ticket_gemv = st->ticket_xr = st->ticket_misc = 0u;
         st->rrn_ready = 0u;
+        for (int k = 0; k < 8; ++k) st->phase_cycles[k] = 0;
         st->seq_base = a.seq_base;
     }
 }

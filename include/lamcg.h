@@ -96,6 +96,7 @@ const char *lamcg_version(void);
  *                the streaming kernel loads with the L2 evict-last policy), persist_rows_smem: tuning of the one-kernel loop
  *  persist_grid  upper bound on the CTAs of the persistent kernel (0: one per SM)
  *  fuse_updates  1 (default): K2 + K3 as one cooperative launch (single rank / peer mode); 0: two launches
+ *  loop_profile  1: stream / graph loop in peer mode: CTA 0 accumulates wait and work cycles per phase (lamcg_get_loop_profile)
  *  spd_simt      1: the SPD generator as in round 1 (SIMT products, recursion to single columns); 0 (default): DMMA + CholeskyQR2 leaves
  *  chunk_iters   iterations per graph launch          time_gemv   0/1 event-time every GEMV (stream mode)
  *  ingest_threads (default 8), ingest_chunk_bytes (default 4 MB): reader threads / staging-chunk size of lamcg_load_matrix
@@ -189,6 +190,8 @@ int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch);
 /* Persistent loop only: SM cycles CTA 0 spent in each phase of the last solve, summed over its iterations.
  * v3: [0] p update  [1] GEMV  [2] row sums + p.Ap exchange  [3] alpha broadcast  [4] x/r update + r.r exchange  [5] beta broadcast.
  * v4: [0] p update  [1] GEMV  [2] row sums + publish  [3] gather of Ap  [4] p.Ap, alpha, r, r.r  [5] beta, stop test.
+ * Stream / graph loop with option loop_profile (peer mode): [0] K1's wait for the peers' p  [2] wait for p.Ap  [3] x, r update + r.r
+ * [4] wait for r.r  [5] beta, p update, peer stores, fence, flags.
  * Returns the count. */
 int lamcg_get_loop_profile(lamcg_t *h, long long *cycles_out, int capacity);
 /* Plain streaming read of this rank's block (sum of all elements): the read-only HBM ceiling the
