@@ -324,7 +324,6 @@ GemvArgs gemv_args(lamcg *h, int check_done, int par)
     g.lda = (long long)h->lda;
     g.row_offset = (long long)h->row_offset;
     g.check_done = check_done;
-    g.prof = h->opt_loop_profile ? 1 : 0;
     return g;
 }
 

@@ -28,7 +28,6 @@ struct GemvArgs {
     long long row_offset; // global index of local row 0 (p is indexed globally)
     int check_done;     // 1 inside the solve loop, 0 for the standalone GEMV hook
     int par;            // iteration parity (scalar double-buffer slot, peer slot / p buffer)
-    int prof;           // 1: CTA 0 adds the SM cycles it waits for the peers' p to st->phase_cycles[0] (option loop_profile)
     PeerView pv;        // pv.nranks <= 1: no peer exchange
 };
 
@@ -42,13 +41,9 @@ __device__ __forceinline__ bool gemv_peer_prologue(const GemvArgs &g, unsigned l
     const int it = g.st->iter[g.par];
     const unsigned long long base = g.st->seq_base;
     seq = base + (unsigned long long)it + 1ull;
-    if (it >= 1) {
-        const bool prof = g.prof && blockIdx.x == 0 && threadIdx.x == 0;
-        const long long tc = prof ? clock64() : 0;
-        const bool ok = peer_wait_all(peer_hdr(g.pv, g.pv.me)->p_flag, g.pv.nranks, base + (unsigned long long)it, g.st, g.pv.timeout_cycles);
-        if (prof) g.st->phase_cycles[0] += clock64() - tc; // K1: wait for every rank's slice of p
-        return ok;
-    }
+    // (not instrumented for option loop_profile: the extra live values cost the 128-register row sweep a spill; the wait was
+    // measured once at 0.3-0.9 us per iteration on 8 GPUs, profiles/r02_mgpu_profile_n100k_8gpu.log)
+    if (it >= 1) return peer_wait_all(peer_hdr(g.pv, g.pv.me)->p_flag, g.pv.nranks, base + (unsigned long long)it, g.st, g.pv.timeout_cycles);
     return true;
 }
 

@@ -190,8 +190,8 @@ int lamcg_time_gemv(lamcg_t *h, int warmup, int reps, double *ms_per_launch);
 /* Persistent loop only: SM cycles CTA 0 spent in each phase of the last solve, summed over its iterations.
  * v3: [0] p update  [1] GEMV  [2] row sums + p.Ap exchange  [3] alpha broadcast  [4] x/r update + r.r exchange  [5] beta broadcast.
  * v4: [0] p update  [1] GEMV  [2] row sums + publish  [3] gather of Ap  [4] p.Ap, alpha, r, r.r  [5] beta, stop test.
- * Stream / graph loop with option loop_profile (peer mode): [0] K1's wait for the peers' p  [2] wait for p.Ap  [3] x, r update + r.r
- * [4] wait for r.r  [5] beta, p update, peer stores, fence, flags.
+ * Stream / graph loop with option loop_profile (peer mode): [2] wait for p.Ap  [3] x, r update + r.r  [4] wait for r.r
+ * [5] beta, p update, peer stores, fence, flags.
  * Returns the count. */
 int lamcg_get_loop_profile(lamcg_t *h, long long *cycles_out, int capacity);
 /* Plain streaming read of this rank's block (sum of all elements): the read-only HBM ceiling the

@@ -32,7 +32,7 @@ for name, opts in (("graph", {"loop_mode": 2, "time_gemv": 0}), ("stream+events"
     prof = s.loop_profile()
     mhz = 1965.0
     out[name] = {"us_per_iteration": 1e6 * r.solve_seconds / r.iterations_run, "gemv_us": 1e6 * r.gemv_seconds / r.iterations_run,
-                 "wait_p_us": prof[0] / iters / mhz, "wait_pAp_us": prof[2] / iters / mhz, "xr_work_us": prof[3] / iters / mhz,
+                 "wait_pAp_us": prof[2] / iters / mhz, "xr_work_us": prof[3] / iters / mhz,
                  "wait_rr_us": prof[4] / iters / mhz, "p_phase_us": prof[5] / iters / mhz}
 allout = [None] * world
 dist.all_gather_object(allout, out)
