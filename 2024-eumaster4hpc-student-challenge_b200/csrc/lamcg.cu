@@ -111,6 +111,10 @@ struct lamcg {
 
     // graph cache
     cudaGraphExec_t graph_exec = nullptr;
+    // graph loop with per-GEMV timing (loop_mode 2 + time_gemv 1): two executables launched alternately, each with its own
+    // externally recorded events around every K1, so that a chunk's events can be read while the next chunk runs
+    cudaGraphExec_t graph_exec_timed[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> graph_events[2];
     int graph_chunk = 0;
     int graph_variant = 0;
     int graph_comm = -1;
@@ -230,6 +234,13 @@ int make_plan(lamcg *h)
     return LAMCG_OK;
 }
 
+void destroy_graphs(lamcg *h)
+{
+    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    for (int k = 0; k < 2; ++k)
+        if (h->graph_exec_timed[k]) { cudaGraphExecDestroy(h->graph_exec_timed[k]); h->graph_exec_timed[k] = nullptr; }
+}
+
 // Unmap every peer exchange buffer this rank has opened (also the partial set of a failed lamcg_comm_init_peer).
 void close_peer_handles(lamcg *h)
 {
@@ -248,7 +259,7 @@ long long peer_timeout_cycles(const lamcg *h)
 void free_system(lamcg *h)
 {
     cudaSetDevice(h->device);
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    destroy_graphs(h);
     cudaFree(h->A); cudaFree(h->b_full); cudaFree(h->x); cudaFree(h->r); cudaFree(h->Ap);
     cudaFree(h->p_full); cudaFree(h->x_full);
     h->A = h->b_full = h->x = h->r = h->Ap = h->p_full = h->x_full = nullptr;
@@ -384,13 +395,15 @@ int allgather_vec(lamcg *h, char *full)
 }
 
 // One CG iteration enqueued on h->stream (also the body captured into the CUDA graph).
-int enqueue_iteration(lamcg *h, int par, cudaEvent_t ev0, cudaEvent_t ev1, int *launches)
+int enqueue_iteration(lamcg *h, int par, cudaEvent_t ev0, cudaEvent_t ev1, int *launches, bool capturing = false)
 {
     NcclApi &N = nccl_api();
-    if (ev0) CK(cudaEventRecord(ev0, h->stream));
+    // inside a stream capture an event record must be flagged external to become a record NODE (a timestamp at every replay)
+    const unsigned int evflags = capturing ? cudaEventRecordExternal : cudaEventRecordDefault;
+    if (ev0) CK(cudaEventRecordWithFlags(ev0, h->stream, evflags));
     int rc = launch_gemv(h, 1, par);
     if (rc != LAMCG_OK) return rc;
-    if (ev1) CK(cudaEventRecord(ev1, h->stream));
+    if (ev1) CK(cudaEventRecordWithFlags(ev1, h->stream, evflags));
     if (h->comm_mode == kCommNccl)
         NCK(N.AllReduce(&h->st->pAp_local, &h->st->pAp, 1, ncclDouble, ncclSum, h->nccl, h->stream));
     VecArgs v = vec_args(h, par);
@@ -418,21 +431,47 @@ int enqueue_iteration(lamcg *h, int par, cudaEvent_t ev0, cudaEvent_t ev1, int *
     return LAMCG_OK;
 }
 
-int build_graph(lamcg *h, int chunk)
+// Capture `chunk` iterations into one executable graph; timed_slot >= 0: with external event records around every K1
+int capture_chunk(lamcg *h, int chunk, int timed_slot, cudaGraphExec_t *exec_out)
 {
-    if (h->graph_exec && h->graph_chunk == chunk && h->graph_variant == h->plan.variant && h->graph_n == h->n && h->graph_comm == h->comm_mode) return LAMCG_OK;
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    if (timed_slot >= 0) {
+        std::vector<cudaEvent_t> &ev = h->graph_events[timed_slot];
+        while ((int)ev.size() < 2 * chunk) {
+            cudaEvent_t e;
+            CK(cudaEventCreate(&e));
+            ev.push_back(e);
+        }
+    }
     cudaGraph_t graph = nullptr;
     CK(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
     int dummy = 0;
     int rc = LAMCG_OK;
-    for (int i = 0; i < chunk && rc == LAMCG_OK; ++i) rc = enqueue_iteration(h, i & 1, nullptr, nullptr, &dummy);
+    for (int i = 0; i < chunk && rc == LAMCG_OK; ++i) {
+        cudaEvent_t e0 = timed_slot >= 0 ? h->graph_events[timed_slot][2 * i] : nullptr;
+        cudaEvent_t e1 = timed_slot >= 0 ? h->graph_events[timed_slot][2 * i + 1] : nullptr;
+        rc = enqueue_iteration(h, i & 1, e0, e1, &dummy, true);
+    }
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
     if (rc != LAMCG_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
     if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&h->graph_exec, graph, 0);
+    e = cudaGraphInstantiate(exec_out, graph, 0);
     cudaGraphDestroy(graph);
     if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return LAMCG_OK;
+}
+
+int build_graph(lamcg *h, int chunk, bool timed)
+{
+    const bool same = h->graph_chunk == chunk && h->graph_variant == h->plan.variant && h->graph_n == h->n && h->graph_comm == h->comm_mode;
+    if (!same) destroy_graphs(h);
+    int rc = LAMCG_OK;
+    if (timed) {
+        for (int k = 0; k < 2 && rc == LAMCG_OK; ++k)
+            if (!h->graph_exec_timed[k]) rc = capture_chunk(h, chunk, k, &h->graph_exec_timed[k]);
+    } else if (!h->graph_exec) {
+        rc = capture_chunk(h, chunk, -1, &h->graph_exec);
+    }
+    if (rc != LAMCG_OK) return rc;
     h->graph_chunk = chunk;
     h->graph_variant = h->plan.variant;
     h->graph_comm = h->comm_mode;
@@ -454,7 +493,7 @@ int ensure_hist(lamcg *h, int max_iters, int keep)
     cudaFree(h->hist);
     h->hist = grown;
     h->hist_cap = want;
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; } // hist pointer is baked in
+    destroy_graphs(h); // hist pointer is baked in
     return LAMCG_OK;
 }
 
@@ -654,7 +693,9 @@ int resolve_loop_mode(lamcg *h)
         else if (h->nranks == 1 && h->dtype == 0 && h->n <= kPersistAutoMaxN) loop_mode = kLoopPersistent;
         else loop_mode = kLoopGraph;
     }
-    if (h->opt_time_gemv) loop_mode = kLoopStream;
+    // per-GEMV timing: stream launches with events around every K1, or (loop_mode 2 asked for explicitly) the graph loop with
+    // externally recorded events inside the captured chunks; the one-kernel loop has no GEMV launches to time
+    if (h->opt_time_gemv && loop_mode != kLoopGraph) loop_mode = kLoopStream;
     return loop_mode;
 }
 
@@ -666,12 +707,22 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
     int chunk = (int)std::max<long long>(2, h->opt_chunk_iters);
     chunk += chunk & 1; // the parity double-buffering needs an even number of iterations per chunk
     int rc;
+    const bool time_gemv = h->opt_time_gemv != 0 && max_total > first_iter;
+    const bool graph_timed = time_gemv && loop_mode == kLoopGraph;
     if (loop_mode == kLoopGraph) {
-        rc = build_graph(h, chunk);
+        rc = build_graph(h, chunk, graph_timed);
         if (rc != LAMCG_OK) return rc;
     }
-    const bool time_gemv = h->opt_time_gemv != 0 && max_total > first_iter;
-    if (time_gemv) {
+    std::vector<float> graph_gemv_ms; // graph_timed: per-iteration K1 durations in launch order
+    auto read_graph_events = [&](int slot) { // the chunk launched from executable `slot` has completed
+        for (int i = 0; i < chunk; ++i) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, h->graph_events[slot][2 * i], h->graph_events[slot][2 * i + 1]) != cudaSuccess) { cudaGetLastError(); t = 0.f; }
+            graph_gemv_ms.push_back(t);
+        }
+    };
+    std::vector<int> chunk_slot; // per enqueued chunk c: timed executable it was launched from, or -1
+    if (time_gemv && !graph_timed) {
         const size_t need = 2 * (size_t)std::min(max_total - first_iter, 1 << 16);
         while (h->gemv_events.size() < need) {
             cudaEvent_t e;
@@ -684,15 +735,18 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
     bool stop = false;
     while (launched < max_total && !stop) {
         if (loop_mode == kLoopGraph && (launched & 1) == 0) {
-            CK(cudaGraphLaunch(h->graph_exec, h->stream)); // the captured chunk starts on parity 0
+            const int slot = graph_timed ? (int)(chunk_slot.size() & 1) : -1;
+            CK(cudaGraphLaunch(graph_timed ? h->graph_exec_timed[slot] : h->graph_exec, h->stream)); // the captured chunk starts on parity 0
+            chunk_slot.push_back(slot);
             launched += chunk;
             launches += (fuse_updates(h) ? 2 : 3) * chunk;
         } else {
+            chunk_slot.push_back(-1);
             const int count = loop_mode == kLoopGraph ? 1 : chunk; // graph loop resumed on an odd iteration: one plain step first
             for (int i = 0; i < count && launched < max_total; ++i, ++launched) {
                 cudaEvent_t e0 = nullptr, e1 = nullptr;
                 const size_t k = (size_t)(launched - first_iter);
-                if (time_gemv && 2 * k + 1 < h->gemv_events.size()) {
+                if (time_gemv && !graph_timed && 2 * k + 1 < h->gemv_events.size()) {
                     e0 = h->gemv_events[2 * k];
                     e1 = h->gemv_events[2 * k + 1];
                     timed_iters = (int)k + 1;
@@ -707,6 +761,7 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
             CK(cudaEventSynchronize(h->ev_ring[(c - 1) & 1]));
             const DevState &s = h->h_st[(c - 1) & 1];
             if (s.done || s.error) stop = true;
+            if (chunk_slot[c - 1] >= 0) read_graph_events(chunk_slot[c - 1]); // chunk c (the other executable) is running, c + 1 not yet launched
         }
         ++c;
     }
@@ -721,7 +776,11 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
     double gemv_ms = 0.0;
-    if (time_gemv) {
+    if (graph_timed) {
+        if (c >= 1 && chunk_slot[c - 1] >= 0) read_graph_events(chunk_slot[c - 1]); // the last chunk (the stream is idle now)
+        const int cnt = std::min((int)graph_gemv_ms.size(), s.iters_done - first_iter); // launches after `done` are no-ops: not counted
+        for (int i = 0; i < cnt; ++i) gemv_ms += graph_gemv_ms[i];
+    } else if (time_gemv) {
         const int cnt = std::min(timed_iters, s.iters_done - first_iter);
         for (int i = 0; i < cnt; ++i) {
             float t = 0.f;
@@ -877,7 +936,7 @@ void lamcg_destroy(lamcg_t *h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     // A CUDA graph that captured NCCL kernels keeps the communicator referenced: ncclCommDestroy
     // blocks until such graphs are gone, so the executable graph goes first.
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    destroy_graphs(h);
     if (h->nccl) nccl_api().CommDestroy(h->nccl);
     close_peer_handles(h);
     cudaFree(h->peer_base);
@@ -885,6 +944,8 @@ void lamcg_destroy(lamcg_t *h)
     if (h->ingest_pool) cudaFreeHost(h->ingest_pool);
     free_system(h);
     for (cudaEvent_t e : h->gemv_events) cudaEventDestroy(e);
+    for (int k = 0; k < 2; ++k)
+        for (cudaEvent_t e : h->graph_events[k]) cudaEventDestroy(e);
     cudaFree(h->hist);
     cudaFree(h->st);
     cudaFree(h->partials);
@@ -920,7 +981,7 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "fuse_updates") h->opt_fuse_updates = value;
     else if (k == "loop_profile") h->opt_loop_profile = value;
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    destroy_graphs(h);
     if (h->alloc_n) {
         CK(cudaSetDevice(h->device));
         return make_plan(h);
@@ -1056,7 +1117,7 @@ int lamcg_comm_init_peer(lamcg_t *h, const void *all_handles)
     h->pv.me = h->rank;
     h->pv.nranks = h->nranks;
     h->comm_mode = kCommPeer;
-    if (h->graph_exec) { cudaGraphExecDestroy(h->graph_exec); h->graph_exec = nullptr; }
+    destroy_graphs(h);
     return LAMCG_OK;
 }
 

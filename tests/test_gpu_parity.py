@@ -330,6 +330,33 @@ def test_stream_and_graph_loops_are_bit_identical_and_reproducible(solver):
         assert it == results[0][0] and rel == results[0][1] and np.array_equal(x, results[0][2])
 
 
+def test_graph_loop_times_every_gemv_like_the_stream_loop(solver):
+    """loop_mode 2 + time_gemv 1: external event-record nodes around every K1 inside the captured chunks (two executables
+    launched alternately so a chunk's events can be read while the next one runs).  Same bits as the untimed loops, a GEMV time
+    that agrees with the stream loop's, and launches after convergence (no-ops) are not counted."""
+    n = 20000
+    solver.generate_matrix(n, n)
+    solver.generate_rhs()
+    res = {}
+    for name, opts in (("stream", {"loop_mode": 1, "time_gemv": 1}), ("graph_timed", {"loop_mode": 2, "time_gemv": 1}), ("graph", {"loop_mode": 2, "time_gemv": 0})):
+        for k, v in opts.items():
+            solver.set_option(k, v)
+        solver.solve(100, 1e-9)
+        r = solver.solve(100, 1e-9)
+        res[name] = (r, solver.solution().copy())
+    assert np.array_equal(res["stream"][1], res["graph_timed"][1]) and np.array_equal(res["graph"][1], res["graph_timed"][1])
+    gs, gg = res["stream"][0].gemv_seconds / 100, res["graph_timed"][0].gemv_seconds / 100
+    assert res["graph"][0].gemv_seconds == 0.0 and gs > 0 and abs(gg - gs) <= 0.05 * gs, (gs, gg)
+    assert gg <= res["graph_timed"][0].solve_seconds / 100                       # a part of the iteration, not more
+    # converges at iteration 500 of n = 1000, in the middle of a 16-iteration chunk: only executed GEMVs are timed
+    solver.set_option("loop_mode", 2)
+    solver.set_option("time_gemv", 1)
+    solver.generate_matrix(1000, 1000)
+    solver.generate_rhs()
+    r = solver.solve(10000, 1e-9)
+    assert r.converged and r.iterations == 500 and 0 < r.gemv_seconds < r.solve_seconds
+
+
 def test_graph_chunking_does_not_overshoot(solver):
     """max_iters not a multiple of the graph chunk, and convergence in the middle of a chunk."""
     n = 512
