@@ -46,7 +46,8 @@ class LamcgError(RuntimeError):
 class lamcg_result(ctypes.Structure):
     _fields_ = [("converged", ctypes.c_int), ("iterations", ctypes.c_int), ("rel_residual", ctypes.c_double),
                 ("solve_seconds", ctypes.c_double), ("gemv_seconds", ctypes.c_double),
-                ("iterations_run", ctypes.c_int), ("kernel_launches", ctypes.c_int), ("numerical_breakdown", ctypes.c_int)]
+                ("iterations_run", ctypes.c_int), ("kernel_launches", ctypes.c_int), ("numerical_breakdown", ctypes.c_int),
+                ("gemv_launches_timed", ctypes.c_int)]
 
 
 class lamcg_info(ctypes.Structure):

@@ -447,8 +447,11 @@ int capture_chunk(lamcg *h, int chunk, int timed_slot, cudaGraphExec_t *exec_out
     int dummy = 0;
     int rc = LAMCG_OK;
     for (int i = 0; i < chunk && rc == LAMCG_OK; ++i) {
-        cudaEvent_t e0 = timed_slot >= 0 ? h->graph_events[timed_slot][2 * i] : nullptr;
-        cudaEvent_t e1 = timed_slot >= 0 ? h->graph_events[timed_slot][2 * i + 1] : nullptr;
+        // time_gemv 1: events around every K1 of the chunk; time_gemv >= 2: around ONE K1 in the middle of the chunk (an event-record
+        // node between two kernels costs ~7 us on a busy 8-GPU box: 14 us per iteration with events around every K1, measured)
+        const bool timed = timed_slot >= 0 && (h->opt_time_gemv == 1 || i == chunk / 2);
+        cudaEvent_t e0 = timed ? h->graph_events[timed_slot][2 * i] : nullptr;
+        cudaEvent_t e1 = timed ? h->graph_events[timed_slot][2 * i + 1] : nullptr;
         rc = enqueue_iteration(h, i & 1, e0, e1, &dummy, true);
     }
     cudaError_t e = cudaStreamEndCapture(h->stream, &graph);
@@ -630,6 +633,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
         out->iterations_run = s.iters_done;
         out->kernel_launches = 1;
         out->numerical_breakdown = s.breakdown;
+        out->gemv_launches_timed = 0;
     }
     return LAMCG_OK;
 }
@@ -713,11 +717,12 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
         rc = build_graph(h, chunk, graph_timed);
         if (rc != LAMCG_OK) return rc;
     }
-    std::vector<float> graph_gemv_ms; // graph_timed: per-iteration K1 durations in launch order
+    std::vector<float> graph_gemv_ms; // graph_timed: per-iteration K1 durations in launch order (-1: launch not timed)
     auto read_graph_events = [&](int slot) { // the chunk launched from executable `slot` has completed
         for (int i = 0; i < chunk; ++i) {
-            float t = 0.f;
-            if (cudaEventElapsedTime(&t, h->graph_events[slot][2 * i], h->graph_events[slot][2 * i + 1]) != cudaSuccess) { cudaGetLastError(); t = 0.f; }
+            float t = -1.f;
+            if (h->opt_time_gemv == 1 || i == chunk / 2)
+                if (cudaEventElapsedTime(&t, h->graph_events[slot][2 * i], h->graph_events[slot][2 * i + 1]) != cudaSuccess) { cudaGetLastError(); t = -1.f; }
             graph_gemv_ms.push_back(t);
         }
     };
@@ -776,12 +781,15 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
     float ms = 0.f;
     CK(cudaEventElapsedTime(&ms, h->ev_start, h->ev_stop));
     double gemv_ms = 0.0;
+    int gemv_timed = 0; // GEMV launches the sum covers
     if (graph_timed) {
         if (c >= 1 && chunk_slot[c - 1] >= 0) read_graph_events(chunk_slot[c - 1]); // the last chunk (the stream is idle now)
         const int cnt = std::min((int)graph_gemv_ms.size(), s.iters_done - first_iter); // launches after `done` are no-ops: not counted
-        for (int i = 0; i < cnt; ++i) gemv_ms += graph_gemv_ms[i];
+        for (int i = 0; i < cnt; ++i)
+            if (graph_gemv_ms[i] >= 0.f) { gemv_ms += graph_gemv_ms[i]; ++gemv_timed; }
     } else if (time_gemv) {
         const int cnt = std::min(timed_iters, s.iters_done - first_iter);
+        gemv_timed = cnt;
         for (int i = 0; i < cnt; ++i) {
             float t = 0.f;
             CK(cudaEventElapsedTime(&t, h->gemv_events[2 * i], h->gemv_events[2 * i + 1]));
@@ -801,6 +809,7 @@ int run_loop(lamcg *h, int loop_mode, int first_iter, int max_total, lamcg_resul
         out->iterations_run = s.iters_done;
         out->kernel_launches = launches;
         out->numerical_breakdown = s.breakdown;
+        out->gemv_launches_timed = gemv_timed;
     }
     return LAMCG_OK;
 }

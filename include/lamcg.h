@@ -48,11 +48,13 @@ typedef struct {
                               (the reference's loop variable after exit, MPI_OMP.hpp:125) */
     double rel_residual;   /* sqrt(rr/bb) at exit */
     double solve_seconds;  /* device time of the iteration loop (CUDA events) */
-    double gemv_seconds;   /* summed device time of the GEMV launches; 0 unless option time_gemv=1 */
+    double gemv_seconds;   /* summed device time of the timed GEMV launches (gemv_launches_timed of them); 0 unless option time_gemv */
     int iterations_run;    /* iterations actually executed on the device (== min(iterations,max_iters)) */
     int kernel_launches;   /* kernels of this library launched by this solve (incl. graph nodes) */
     int numerical_breakdown; /* 1: stopped early on a non-finite residual (b = 0, A not SPD): reported like the
                               reference would after max_iters NaN iterations: converged 0, max_iters+1, nan */
+    int gemv_launches_timed; /* how many GEMV launches gemv_seconds sums over: every executed one with time_gemv = 1, one per
+                              graph chunk with loop_mode 2 and time_gemv >= 2 */
 } lamcg_result;
 
 typedef struct {
@@ -98,7 +100,9 @@ const char *lamcg_version(void);
  *  fuse_updates  1 (default): K2 + K3 as one cooperative launch (single rank / peer mode); 0: two launches
  *  loop_profile  1: stream / graph loop in peer mode: CTA 0 accumulates wait and work cycles per phase (lamcg_get_loop_profile)
  *  spd_simt      1: the SPD generator as in round 1 (SIMT products, recursion to single columns); 0 (default): DMMA + CholeskyQR2 leaves
- *  chunk_iters   iterations per graph launch          time_gemv   0/1 event-time every GEMV (stream mode)
+ *  chunk_iters   iterations per graph launch
+ *  time_gemv     1: CUDA events around every GEMV launch (stream loop; with loop_mode 2 as event-record nodes inside the graph);
+ *                2 with loop_mode 2: around one GEMV per graph chunk (an event node between two kernels is not free)
  *  ingest_threads (default 8), ingest_chunk_bytes (default 4 MB): reader threads / staging-chunk size of lamcg_load_matrix
  *  peer_timeout_s (default 600): bound of every in-kernel wait for a peer rank; on expiry the solve returns LAMCG_ERR_DEVICE
  *  gemv_ctas_per_sm  tuning override     history  0/1 keep sqrt(rr/bb) per iteration (default 1)

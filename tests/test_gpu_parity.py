@@ -346,8 +346,14 @@ def test_graph_loop_times_every_gemv_like_the_stream_loop(solver):
         res[name] = (r, solver.solution().copy())
     assert np.array_equal(res["stream"][1], res["graph_timed"][1]) and np.array_equal(res["graph"][1], res["graph_timed"][1])
     gs, gg = res["stream"][0].gemv_seconds / 100, res["graph_timed"][0].gemv_seconds / 100
+    assert res["stream"][0].gemv_launches_timed == res["graph_timed"][0].gemv_launches_timed == 100
     assert res["graph"][0].gemv_seconds == 0.0 and gs > 0 and abs(gg - gs) <= 0.05 * gs, (gs, gg)
     assert gg <= res["graph_timed"][0].solve_seconds / 100                       # a part of the iteration, not more
+    solver.set_option("loop_mode", 2)
+    solver.set_option("time_gemv", 2)                                            # one GEMV per 16-iteration chunk
+    r = solver.solve(100, 1e-9)
+    assert r.gemv_launches_timed == 6 and abs(r.gemv_seconds / 6 - gs) <= 0.05 * gs   # chunks 0..5 have their sampled launch (8, 24, .. 88) below 100
+    assert np.array_equal(solver.solution(), res["stream"][1])
     # converges at iteration 500 of n = 1000, in the middle of a 16-iteration chunk: only executed GEMVs are timed
     solver.set_option("loop_mode", 2)
     solver.set_option("time_gemv", 1)
