@@ -56,7 +56,8 @@ class lamcg_info(ctypes.Structure):
                 ("sm_count", ctypes.c_int), ("comm_mode", ctypes.c_int), ("has_matrix", ctypes.c_int),
                 ("has_rhs", ctypes.c_int), ("gemv_variant", ctypes.c_int), ("gemv_grid", ctypes.c_int),
                 ("gemv_block", ctypes.c_int), ("gemv_smem_bytes", ctypes.c_int), ("dtype", ctypes.c_int),
-                ("ingest_threads", ctypes.c_int), ("ingest_chunks", ctypes.c_int)]
+                ("ingest_threads", ctypes.c_int), ("ingest_chunks", ctypes.c_int), ("matrix_elem_bytes", ctypes.c_int),
+                ("matrix_f32_inexact", ctypes.c_ulonglong), ("matrix_f32_overflow", ctypes.c_ulonglong)]
 
 
 def build(verbose: bool = False) -> str:

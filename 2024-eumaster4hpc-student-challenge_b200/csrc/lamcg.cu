@@ -65,6 +65,9 @@ struct lamcg {
     size_t alloc_n = 0;
     int dtype = 0;                 // 0 = fp64 (the hot path), 1 = fp32 storage (reductions and scalars stay fp64)
     size_t esz = sizeof(double);   // bytes per stored element
+    size_t asz = sizeof(double);   // bytes per stored MATRIX element: esz, or 4 under option matrix_f32 on an fp64 handle
+    unsigned long long *narrow_stats = nullptr; // device [2]: inexact / overflowed entries of the last fp64 -> fp32 matrix ingest
+    unsigned long long last_inexact = 0, last_overflow = 0;
     // byte pointers: element type is `dtype`
     char *A = nullptr, *b_full = nullptr, *x = nullptr, *r = nullptr, *Ap = nullptr, *p_full = nullptr;
     char *x_full = nullptr; // gather target for get_solution (multi-rank), [lda]
@@ -86,6 +89,7 @@ struct lamcg {
     long long opt_loop_profile = 0;       // multi-rank stream / graph loop: CTA 0 of K1 / K2+K3 accumulates wait and work cycles (lamcg_get_loop_profile)
     long long opt_fuse_updates = 1;       // K2 + K3 in one cooperative launch (single rank / peer mode)
     long long opt_spd_simt = 0;           // 1: the SPD generator's products on the SIMT kernel only (comparison / fallback)
+    long long opt_matrix_f32 = 0;         // 1 (fp64 handles): the matrix is held in HBM as fp32, everything else stays fp64
     int clock_khz = 1965000;
     char *ingest_pool = nullptr;          // pinned staging buffers of the file ingest (kept between loads)
     size_t ingest_pool_bytes = 0;
@@ -178,7 +182,10 @@ bool plan_rowsweep(lamcg *h, GemvPlan &p, int variant)
 {
     constexpr int R = 8;
     p.variant = variant;
-    if (h->dtype == 0) p.kernel = lamcg_rowsweep_kernel<double, R, U, NT, CPS, VB>;
+    if (h->asz != h->esz) {
+        if constexpr (VB == 16) p.kernel = lamcg_rowsweep_kernel<double, R, U, NT, CPS, VB, float>;
+        else return false;
+    } else if (h->dtype == 0) p.kernel = lamcg_rowsweep_kernel<double, R, U, NT, CPS, VB>;
     else p.kernel = lamcg_rowsweep_kernel<float, R, U, NT, CPS, VB>;
     p.block = NT;
     p.smem = 0;
@@ -216,6 +223,8 @@ int make_plan(lamcg *h)
     if (v == 0) v = h->local_rows >= 12000 ? 36 : 32;
     if (h->dtype != 0 && (v == 11 || v == 2))
         return h->fail(LAMCG_ERR_INVALID, "gemv_variant %d is fp64 only (fp32 handles use the row-sweep family 32/36/42/46)", v);
+    if (h->asz != h->esz && v != 32 && v != 36)
+        return h->fail(LAMCG_ERR_INVALID, "gemv_variant %d does not read an fp32 matrix (option matrix_f32 runs the row sweeps 32 / 36)", v);
     bool ok = false;
     GemvPlan p;
     switch (v) {
@@ -287,11 +296,11 @@ int alloc_system(lamcg *h, size_t n)
     partition(n, h->nranks, h->rank, &h->local_rows, &h->row_offset);
     h->lda = (n + 15) / 16 * 16; // rows start on 128-byte boundaries; pad columns are zero
     const size_t rows_alloc = std::max<size_t>(h->local_rows, 1);
-    cudaError_t e = cudaMalloc(&h->A, rows_alloc * h->lda * h->esz);
+    cudaError_t e = cudaMalloc(&h->A, rows_alloc * h->lda * h->asz);
     if (e != cudaSuccess) {
         cudaGetLastError();
         return h->fail(LAMCG_ERR_NOMEM, "cudaMalloc of the %zu x %zu row block (%.2f GB) failed: %s", h->local_rows, h->lda,
-                       rows_alloc * h->lda * (double)h->esz / 1e9, cudaGetErrorString(e));
+                       rows_alloc * h->lda * (double)h->asz / 1e9, cudaGetErrorString(e));
     }
     CK(cudaMalloc(&h->b_full, h->lda * h->esz));
     CK(cudaMalloc(&h->p_full, h->lda * h->esz));
@@ -305,6 +314,37 @@ int alloc_system(lamcg *h, size_t n)
     h->alloc_n = n;
     int rc = make_plan(h);
     if (rc != LAMCG_OK) return rc;
+    return LAMCG_OK;
+}
+
+// ---- option matrix_f32: fp64 sources are narrowed on the device into the fp32 matrix block --------------------------------
+bool mixed_storage(const lamcg *h) { return h->asz != h->esz; }
+
+int narrow_begin(lamcg *h)
+{
+    if (!h->narrow_stats) CK(cudaMalloc(&h->narrow_stats, 2 * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(h->narrow_stats, 0, 2 * sizeof(unsigned long long), h->stream));
+    CK(cudaStreamSynchronize(h->stream));
+    return LAMCG_OK;
+}
+
+// rows [first_row, first_row + nr) of the local block from nr fp64 rows in device memory (row pitch src_ld), on stream st
+cudaError_t narrow_rows(lamcg *h, const double *dev_src, size_t src_ld, size_t first_row, size_t nr, cudaStream_t st)
+{
+    if (nr == 0) return cudaSuccess;
+    const long long total = (long long)nr * (long long)((h->n + 1) / 2);
+    const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 8);
+    narrow_rows_kernel<<<grid, 256, 0, st>>>(dev_src, (long long)src_ld, reinterpret_cast<float *>(h->A) + first_row * h->lda, (long long)h->lda,
+                                             (long long)nr, (long long)h->n, h->narrow_stats);
+    return cudaGetLastError();
+}
+
+int narrow_end(lamcg *h)
+{
+    unsigned long long st[2] = {0, 0};
+    CK(cudaMemcpy(st, h->narrow_stats, sizeof st, cudaMemcpyDeviceToHost));
+    h->last_inexact = st[0];
+    h->last_overflow = st[1];
     return LAMCG_OK;
 }
 
@@ -511,6 +551,7 @@ int solve_persistent(lamcg *h, int max_iters, double rel_error, lamcg_result *ou
 {
     if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "the persistent loop is single-rank");
     if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "the persistent loop is fp64 only");
+    if (mixed_storage(h)) return h->fail(LAMCG_ERR_INVALID, "the persistent loop reads an fp64 matrix (option matrix_f32 is on)");
     if (h->n > kPersistMaxN) return h->fail(LAMCG_ERR_INVALID, "the persistent loop supports n <= %zu", kPersistMaxN);
 
     int grid = (int)std::min<size_t>(std::min<size_t>((size_t)h->sm_count, (size_t)kPersistMaxGrid), h->n);
@@ -694,7 +735,7 @@ int resolve_loop_mode(lamcg *h)
     int loop_mode = (int)h->opt_loop_mode;
     if (loop_mode == kLoopAuto) {
         if (h->opt_time_gemv) loop_mode = kLoopStream;
-        else if (h->nranks == 1 && h->dtype == 0 && h->n <= kPersistAutoMaxN) loop_mode = kLoopPersistent;
+        else if (h->nranks == 1 && h->dtype == 0 && !mixed_storage(h) && h->n <= kPersistAutoMaxN) loop_mode = kLoopPersistent;
         else loop_mode = kLoopGraph;
     }
     // per-GEMV timing: stream launches with events around every K1, or (loop_mode 2 asked for explicitly) the graph loop with
@@ -918,6 +959,8 @@ int lamcg_create_ranked(lamcg_t **out, int device, int rank, int nranks)
     h->opt_ingest_chunk_bytes = env_ll("ingest_chunk_bytes", 4ll << 20);
     h->opt_peer_timeout_s = env_ll("peer_timeout_s", 600);
     h->opt_persist_grid = env_ll("persist_grid", 0);
+    h->opt_matrix_f32 = env_ll("matrix_f32", 0) == 1 ? 1 : 0;
+    h->asz = h->opt_matrix_f32 ? sizeof(float) : sizeof(double);
     *out = h;
     return LAMCG_OK;
 }
@@ -935,6 +978,8 @@ int lamcg_create_typed(lamcg_t **out, int device, int rank, int nranks, int dtyp
     if (rc != LAMCG_OK) return rc;
     (*out)->dtype = dtype;
     (*out)->esz = dtype == 0 ? sizeof(double) : sizeof(float);
+    if (dtype != 0) (*out)->opt_matrix_f32 = 0; // an fp32 handle already stores fp32
+    (*out)->asz = (*out)->opt_matrix_f32 ? sizeof(float) : (*out)->esz;
     return LAMCG_OK;
 }
 
@@ -950,6 +995,7 @@ void lamcg_destroy(lamcg_t *h)
     close_peer_handles(h);
     cudaFree(h->peer_base);
     cudaFree(h->persist_ll);
+    cudaFree(h->narrow_stats);
     if (h->ingest_pool) cudaFreeHost(h->ingest_pool);
     free_system(h);
     for (cudaEvent_t e : h->gemv_events) cudaEventDestroy(e);
@@ -971,6 +1017,7 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
 {
     if (!h || !key) return LAMCG_ERR_INVALID;
     std::string k(key);
+    const long long old_variant = h->opt_gemv_variant;
     if (k == "gemv_variant") h->opt_gemv_variant = value;
     else if (k == "loop_mode") h->opt_loop_mode = value;
     else if (k == "chunk_iters") h->opt_chunk_iters = value;
@@ -989,11 +1036,25 @@ int lamcg_set_option(lamcg_t *h, const char *key, long long value)
     else if (k == "spd_simt") h->opt_spd_simt = value;
     else if (k == "fuse_updates") h->opt_fuse_updates = value;
     else if (k == "loop_profile") h->opt_loop_profile = value;
+    else if (k == "matrix_f32") {
+        if (value != 0 && value != 1) return h->fail(LAMCG_ERR_INVALID, "matrix_f32 is 0 or 1");
+        if (value && h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "matrix_f32 applies to fp64 handles (an fp32 handle already stores fp32)");
+        if (value != h->opt_matrix_f32) {
+            // the matrix block changes its element size: whatever system is loaded is dropped and has to be loaded again
+            free_system(h);
+            h->resumable = false;
+            h->opt_matrix_f32 = value;
+            h->asz = value ? sizeof(float) : h->esz;
+            h->last_inexact = h->last_overflow = 0;
+        }
+    }
     else return h->fail(LAMCG_ERR_INVALID, "unknown option '%s'", key);
     destroy_graphs(h);
     if (h->alloc_n) {
         CK(cudaSetDevice(h->device));
-        return make_plan(h);
+        const int rc = make_plan(h);
+        if (rc != LAMCG_OK && k == "gemv_variant") h->opt_gemv_variant = old_variant; // refused: the loaded system keeps its working plan
+        return rc;
     }
     return LAMCG_OK;
 }
@@ -1019,6 +1080,9 @@ int lamcg_get_info(const lamcg_t *h, lamcg_info *out)
     out->dtype = h->dtype;
     out->ingest_threads = h->last_ingest_threads;
     out->ingest_chunks = (int)std::min<long long>(h->last_ingest_chunks, INT_MAX);
+    out->matrix_elem_bytes = (int)h->asz;
+    out->matrix_f32_inexact = h->last_inexact;
+    out->matrix_f32_overflow = h->last_overflow;
     return LAMCG_OK;
 }
 
@@ -1141,7 +1205,7 @@ int lamcg_generate_matrix(lamcg_t *h, size_t rows, size_t cols)
     if (h->local_rows > 0) {
         const long long total = (long long)h->local_rows * (long long)(h->lda / 2);
         const int grid = (int)std::min<long long>((total + 255) / 256, (long long)h->sm_count * 16);
-        if (h->dtype == 0)
+        if (h->dtype == 0 && !mixed_storage(h))
             generate_matrix_kernel<double><<<grid, 256, 0, h->stream>>>(h->A, (long long)h->local_rows, (long long)h->n, (long long)h->lda,
                                                                        (long long)h->row_offset);
         else
@@ -1150,6 +1214,7 @@ int lamcg_generate_matrix(lamcg_t *h, size_t rows, size_t cols)
         CK(cudaGetLastError());
     }
     CK(cudaStreamSynchronize(h->stream));
+    h->last_inexact = h->last_overflow = 0; // 0, 1 and 2 are fp32 numbers
     h->has_matrix = true;
     h->has_rhs = false;
     return LAMCG_OK;
@@ -1177,8 +1242,26 @@ int lamcg_set_matrix(lamcg_t *h, const void *A, size_t n, int layout)
     int rc = alloc_system(h, n);
     if (rc != LAMCG_OK) return rc;
     const char *src = layout == 0 ? static_cast<const char *>(A) + h->row_offset * n * h->esz : static_cast<const char *>(A);
-    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * h->esz, h->stream));
-    if (h->local_rows > 0)
+    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * h->asz, h->stream));
+    if (mixed_storage(h)) {
+        // fp64 source (host or device) -> fp32 block: row chunks of at most 64 MB through a device staging buffer
+        rc = narrow_begin(h);
+        if (rc != LAMCG_OK) return rc;
+        const size_t chunk_rows = std::min(std::max<size_t>(1, ((size_t)64 << 20) / (n * sizeof(double))), std::max<size_t>(h->local_rows, 1));
+        double *stage = nullptr;
+        CK(cudaMalloc(&stage, chunk_rows * n * sizeof(double)));
+        cudaError_t e = cudaSuccess;
+        for (size_t r = 0; r < h->local_rows && e == cudaSuccess; r += chunk_rows) {
+            const size_t nr = std::min(chunk_rows, h->local_rows - r);
+            e = cudaMemcpyAsync(stage, src + r * n * sizeof(double), nr * n * sizeof(double), cudaMemcpyDefault, h->stream);
+            if (e == cudaSuccess) e = narrow_rows(h, stage, n, r, nr, h->stream);
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+        cudaFree(stage);
+        if (e != cudaSuccess) return h->fail(LAMCG_ERR_CUDA, "narrowing the matrix to fp32 failed: %s", cudaGetErrorString(e));
+        rc = narrow_end(h);
+        if (rc != LAMCG_OK) return rc;
+    } else if (h->local_rows > 0)
         CK(cudaMemcpy2DAsync(h->A, h->lda * h->esz, src, n * h->esz, n * h->esz, h->local_rows, cudaMemcpyDefault, h->stream));
     CK(cudaStreamSynchronize(h->stream));
     h->has_matrix = true;
@@ -1234,8 +1317,22 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
     const size_t slot_bytes = chunk_rows * row_bytes;
     rc = ensure_ingest_pool(h, (size_t)T * kIngestSlots * slot_bytes);
     if (rc != LAMCG_OK) { close(fd); return rc; }
-    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * h->esz, h->stream));
+    if (h->lda != n) CK(cudaMemsetAsync(h->A, 0, h->local_rows * h->lda * h->asz, h->stream));
     CK(cudaStreamSynchronize(h->stream));
+    // option matrix_f32: a chunk lands in a device staging slot (one per pinned slot) and is narrowed into the block by a kernel
+    // on the reader's stream; the slot's event then covers both buffers
+    const bool mixed = mixed_storage(h);
+    char *dev_stage = nullptr;
+    if (mixed) {
+        rc = narrow_begin(h);
+        if (rc != LAMCG_OK) { close(fd); return rc; }
+        cudaError_t e = cudaMalloc(&dev_stage, (size_t)T * kIngestSlots * slot_bytes);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            close(fd);
+            return h->fail(LAMCG_ERR_NOMEM, "cudaMalloc of the ingest staging buffers failed: %s", cudaGetErrorString(e));
+        }
+    }
     std::atomic<int> status{LAMCG_OK};
     std::atomic<size_t> next_chunk{0};
     std::string first_error;
@@ -1266,9 +1363,14 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
                                         std::to_string(h->row_offset + r + nr));
                 break;
             }
-            cudaError_t e = cudaMemcpy2DAsync(h->A + r * h->lda * h->esz, h->lda * h->esz, stage, row_bytes, row_bytes, nr,
-                                              cudaMemcpyHostToDevice, st);
-            if (e != cudaSuccess) { failw(LAMCG_ERR_CUDA, std::string("cudaMemcpy2DAsync failed: ") + cudaGetErrorString(e)); break; }
+            cudaError_t e;
+            if (mixed) {
+                char *dstage = dev_stage + ((size_t)t * kIngestSlots + slot) * slot_bytes;
+                e = cudaMemcpyAsync(dstage, stage, nr * row_bytes, cudaMemcpyHostToDevice, st);
+                if (e == cudaSuccess) e = narrow_rows(h, reinterpret_cast<const double *>(dstage), n, r, nr, st);
+            } else
+                e = cudaMemcpy2DAsync(h->A + r * h->lda * h->esz, h->lda * h->esz, stage, row_bytes, row_bytes, nr, cudaMemcpyHostToDevice, st);
+            if (e != cudaSuccess) { failw(LAMCG_ERR_CUDA, std::string("matrix upload failed: ") + cudaGetErrorString(e)); break; }
             cudaEventRecord(done[slot], st);
             slot = (slot + 1) % kIngestSlots;
         }
@@ -1289,7 +1391,12 @@ int lamcg_load_matrix(lamcg_t *h, const char *path)
     h->last_ingest_chunks = (long long)nchunks;
     close(fd);
     CK(cudaSetDevice(h->device));
+    if (dev_stage) cudaFree(dev_stage);
     if (status.load() != LAMCG_OK) return h->fail(status.load(), "%s", first_error.c_str());
+    if (mixed) {
+        rc = narrow_end(h);
+        if (rc != LAMCG_OK) return rc;
+    }
     h->has_matrix = true;
     h->has_rhs = false;
     return LAMCG_OK;
@@ -1731,6 +1838,8 @@ int lamcg_random_spd_system(lamcg_t *h, size_t n, int seed)
     h->resumable = false; // the device state of the last solve no longer matches the system
     if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "the SPD generator runs on one rank (generate, save, then load row blocks)");
     if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "the SPD generator is fp64 only");
+    if (mixed_storage(h))
+        return h->fail(LAMCG_ERR_INVALID, "the SPD generator writes an fp64 matrix block (option matrix_f32 is on: generate with it off, save, then load)");
     int rc = alloc_system(h, n);
     if (rc != LAMCG_OK) return rc;
     CK(cudaFuncSetAttribute(gemm_f64_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMmaSmemBytes));
@@ -1786,6 +1895,7 @@ int lamcg_save_system(lamcg_t *h, const char *matrix_path, const char *rhs_path)
     if (!h || !matrix_path || !rhs_path) return LAMCG_ERR_INVALID;
     if (h->nranks != 1) return h->fail(LAMCG_ERR_INVALID, "save_system runs on one rank");
     if (h->dtype != 0) return h->fail(LAMCG_ERR_INVALID, "save_system is fp64 only");
+    if (mixed_storage(h)) return h->fail(LAMCG_ERR_INVALID, "save_system writes the fp64 matrix block (option matrix_f32 is on)");
     if (!h->has_matrix || !h->has_rhs) return h->fail(LAMCG_ERR_STATE, "no system to save");
     CK(cudaSetDevice(h->device));
     const size_t n = h->n;
@@ -1936,7 +2046,7 @@ int lamcg_time_stream_read(lamcg_t *h, int warmup, int reps, double *ms_per_pass
     if (!h || reps <= 0 || !ms_per_pass) return LAMCG_ERR_INVALID;
     if (!h->has_matrix) return h->fail(LAMCG_ERR_STATE, "no matrix");
     CK(cudaSetDevice(h->device));
-    const long long count2 = (long long)(h->local_rows * h->lda * h->esz / 16);
+    const long long count2 = (long long)(h->local_rows * h->lda * h->asz / 16);
     const int grid = std::min(h->sm_count * 2, kMaxGrid);
     for (int i = 0; i < warmup; ++i) stream_read_kernel<<<grid, kStreamThreads, 0, h->stream>>>(reinterpret_cast<const double *>(h->A), count2, h->partials);
     CK(cudaEventRecord(h->ev_start, h->stream));

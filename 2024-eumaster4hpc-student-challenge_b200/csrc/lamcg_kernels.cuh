@@ -354,6 +354,10 @@ __global__ void __launch_bounds__(kLdgWarps * 32, CPS) lamcg_warprows_tmap_kerne
 // R-row passes; the remaining rows (< R) go through passes of 4, 2 and 1 rows with proportionally MORE loads per row, so every
 // pass keeps the same R*U vector loads in flight per thread: at 12500 rows per GPU (n = 100000 on 8 GPUs, 84-85 rows per CTA)
 // a plain "8 rows, 4 of them masked" last pass ran with half the bytes in flight for ~1/11 of the kernel.
+// Mixed storage (S = float under T = double, option matrix_f32): only the MATRIX is held in fp32; every element is widened to
+// fp64 (exact) before the same unfused multiply and add, so the arithmetic is the fp64 sweep's on the matrix fl32(A) and the
+// HBM stream is half as long.  The widening (F2F.F64.F32) is not a limiter: 7.3 TB/s of fp32 matrix, tools/mixed_probe.cu,
+// profiles/r02_mixed_probe.log.
 // =============================================================================================
 constexpr int kCtaRowMaxR = 8;
 struct kTrue { static constexpr bool value = true; };
@@ -361,13 +365,15 @@ struct kFalse { static constexpr bool value = false; };
 
 // One pass: R rows starting at arow0 (row stride lda), all lda columns.  Returns (warp 0, all lanes) the sum over the R rows of
 // p[row] * Ap[row]; 0.0 in the other warps.  red: [NT/32][kCtaRowMaxR] shared scratch.
-template <typename T, int R, int U, int NT, int VB>
-__device__ __forceinline__ double ctarow_pass(const T *__restrict__ arow0, const T *__restrict__ gp, T *__restrict__ Ap_rs,
+template <typename T, int R, int U, int NT, int VB, typename S = T>
+__device__ __forceinline__ double ctarow_pass(const S *__restrict__ arow0, const T *__restrict__ gp, T *__restrict__ Ap_rs,
                                               const T *__restrict__ p_rs, long long lda, uint64_t polA,
                                               double (*red)[kCtaRowMaxR])
 {
-    constexpr int E = VB / (int)sizeof(T); // elements per load
+    constexpr int E = VB / (int)sizeof(S); // matrix elements per load
+    constexpr int PB = E * (int)sizeof(T); // bytes of p that go with one matrix load
     constexpr int CH = NT * U * E;         // columns per chunk
+    static_assert(PB == 16 || PB == 32, "p is fetched with one 128- or 256-bit load per matrix load");
     constexpr int NWARP = NT / 32;
     static_assert(R <= kCtaRowMaxR, "row sums are finished by one warp from red[][kCtaRowMaxR]");
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -378,29 +384,29 @@ __device__ __forceinline__ double ctarow_pass(const T *__restrict__ arow0, const
     // as (row r-1) + lda by pointer increments and the U loads of a row by immediate offsets, so the full-chunk loop below
     // is loads + 2 integer adds per row (the first version recomputed (row)*lda in 64 bits per load under a predicate:
     // 527 instructions per chunk for 36 loads, profiles/r02_sass_k1_summary.txt).
-    auto chunk = [&](const T *__restrict__ pa, const T *__restrict__ pp, auto pred, long long c_first) {
+    auto chunk = [&](const S *__restrict__ pa, const T *__restrict__ pp, auto pred, long long c_first) {
         constexpr bool kPred = decltype(pred)::value;
-        VecN<T, VB> pv[U];
+        VecN<T, PB> pv[U];
         bool cv[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             cv[u] = !kPred || c_first + (long long)u * NT * E < lda; // lda % 16 == 0 and E <= 8: a vector is all in or all out
-            if (cv[u]) pv[u] = ldg_vec<T, VB>(pp + u * NT * E);
+            if (cv[u]) pv[u] = ldg_vec<T, PB>(pp + u * NT * E);
             else {
 #pragma unroll
                 for (int e = 0; e < E; ++e) pv[u].v[e] = T(0);
             }
         }
-        VecN<T, VB> a[R][U];
-        const T *pr = pa;
+        VecN<S, VB> a[R][U];
+        const S *pr = pa;
 #pragma unroll
         for (int r = 0; r < R; ++r) {
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (cv[u]) a[r][u] = ldg_stream_vec<T, VB>(pr + u * NT * E, polA);
+                if (cv[u]) a[r][u] = ldg_stream_vec<S, VB>(pr + u * NT * E, polA);
                 else {
 #pragma unroll
-                    for (int e = 0; e < E; ++e) a[r][u].v[e] = T(0);
+                    for (int e = 0; e < E; ++e) a[r][u].v[e] = S(0);
                 }
             }
             pr += lda;
@@ -423,12 +429,12 @@ __device__ __forceinline__ double ctarow_pass(const T *__restrict__ arow0, const
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
 #pragma unroll
-                    for (int e = 0; e < E; ++e) acc[r] = prod_acc(a[r][u].v[e], pv[u].v[e], acc[r]);
+                    for (int e = 0; e < E; ++e) acc[r] = prod_acc((T)a[r][u].v[e], pv[u].v[e], acc[r]); // (T): exact widening when S = float
                 }
             }
         }
     };
-    const T *pa = arow0 + E * tid;
+    const S *pa = arow0 + E * tid;
     const T *pp = gp + E * tid;
     const long long nfull = lda / CH;
     for (long long k = 0; k < nfull; ++k, pa += CH, pp += CH) chunk(pa, pp, kFalse{}, 0);
@@ -456,12 +462,15 @@ __device__ __forceinline__ double ctarow_pass(const T *__restrict__ arow0, const
     return contrib;
 }
 
-template <typename T, int R, int U = 4, int NT = 256, int CPS = 2, int VB = 16>
+template <typename T, int R, int U = 4, int NT = 256, int CPS = 2, int VB = 16, typename S = T>
 __global__ void __launch_bounds__(NT, CPS) lamcg_rowsweep_kernel(GemvArgs g)
 {
     static_assert(R == 8, "the tail decomposition below is written for 8-row passes");
+    // widest tail pass: 4*U loads per row; with a narrower matrix type the p registers per load double, so stop at 2*U
+    constexpr int UT = sizeof(S) < sizeof(T) ? 2 * U : 4 * U;
     __shared__ double red[NT / 32][kCtaRowMaxR];
-    const T *gA = static_cast<const T *>(g.A), *gp = static_cast<const T *>(g.p);
+    const S *gA = static_cast<const S *>(g.A);
+    const T *gp = static_cast<const T *>(g.p);
     T *gAp = static_cast<T *>(g.Ap);
     if (g.check_done && ld_volatile_int(&g.st->done)) return;
     unsigned long long seq;
@@ -477,17 +486,17 @@ __global__ void __launch_bounds__(NT, CPS) lamcg_rowsweep_kernel(GemvArgs g)
     long long rs = r0;
     const long long rend = r0 + rcnt;
     for (; rs + R <= rend; rs += R)
-        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, R, U, NT, VB>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
+        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, R, U, NT, VB, S>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
     // tail: < 8 rows left, same number of loads in flight per pass
     if (rs + 4 <= rend) {
-        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 4, 2 * U, NT, VB>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
+        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 4, 2 * U, NT, VB, S>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
         rs += 4;
     }
     if (rs + 2 <= rend) {
-        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 2, 4 * U, NT, VB>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
+        cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 2, UT, NT, VB, S>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
         rs += 2;
     }
-    if (rs < rend) cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 1, 4 * U, NT, VB>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
+    if (rs < rend) cta_dot = __dadd_rn(cta_dot, ctarow_pass<T, 1, UT, NT, VB, S>(gA + rs * g.lda, gp, gAp + rs, prow + rs, g.lda, polA, red));
     if (warp == 0) grid_sum_publish(cta_dot, g.partials, &g.st->ticket_gemv, &g.st->pAp_local, lane, &g.pv, 0, g.par, seq);
 }
 
@@ -833,6 +842,34 @@ __global__ void __launch_bounds__(256) generate_matrix_kernel(void *A_, long lon
         const T v1 = (j + 1 < n) ? (d1 == 0 ? T(2) : ((d1 == 1 || d1 == -1) ? T(1) : T(0))) : T(0);
         A[i * lda + j] = v0;
         A[i * lda + j + 1] = v1;
+    }
+}
+
+// Option matrix_f32: rows of an fp64 source (row pitch src_ld elements) -> the fp32 matrix block (row pitch lda, pad columns
+// already zero).  stats[0] counts the entries whose fp32 value differs from the fp64 one (0 = the mixed-storage solve works on
+// exactly the caller's matrix), stats[1] the finite entries that overflow to infinity.
+__global__ void __launch_bounds__(256) narrow_rows_kernel(const double *__restrict__ src, long long src_ld, float *__restrict__ dst,
+                                                          long long lda, long long rows, long long n, unsigned long long *stats)
+{
+    const long long pairs = (n + 1) >> 1, total = rows * pairs;
+    unsigned int inexact = 0, overflow = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+        const long long i = t / pairs, j = (t - i * pairs) * 2;
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (j + e >= n) break;
+            const double v = src[i * src_ld + j + e];
+            const float f = __double2float_rn(v);
+            dst[i * lda + j + e] = f;
+            if ((double)f != v && v == v) ++inexact; // a NaN stays a NaN: not counted
+            if (isinf(f) && !isinf(v)) ++overflow;
+        }
+    }
+    inexact = __reduce_add_sync(0xffffffffu, inexact);
+    overflow = __reduce_add_sync(0xffffffffu, overflow);
+    if ((threadIdx.x & 31) == 0) {
+        if (inexact) atomicAdd(&stats[0], (unsigned long long)inexact);
+        if (overflow) atomicAdd(&stats[1], (unsigned long long)overflow);
     }
 }
 

@@ -460,8 +460,41 @@ def run_b200_arm(args):
             os.rmdir(tmp)
         return out
 
+    def mixed_storage_case(nn: int, k: int):
+        """Option matrix_f32 (opt-in, NOT the headline): the same generate-mode system with the matrix block held as fp32 (0, 1, 2 are
+        fp32 numbers, so it is the same problem), vectors / products / sums / scalars fp64; same loop engine and GEMV timing as `value`."""
+        sv = make_solver(nn)
+        sv.set_option("matrix_f32", 1)
+        sv.set_option("loop_mode", 2)
+        sv.set_option("time_gemv", 2)
+        sv.generate_matrix(nn, nn)
+        sv.generate_rhs()
+        sv.solve(min(k, 20), 1e-9)
+        barrier()
+        r = sv.solve(k, 1e-9)
+        secs = max_over_ranks(r.solve_seconds)
+        ms = 1e3 * max_over_ranks(r.gemv_seconds) / max(r.gemv_launches_timed, 1)
+        x = sv.solution()
+        inf = sv.info
+        rows = int(inf.local_rows)
+        out = {"n": nn, "ranks": world, "matrix_elem_bytes": int(inf.matrix_elem_bytes), "matrix_GB_per_gpu": 4.0 * rows * nn / 1e9,
+               "entries_rounded": int(inf.matrix_f32_inexact), "gemv_variant": int(inf.gemv_variant),
+               "iterations": int(r.iterations), "rel_residual": r.rel_residual, "iterations_per_s": r.iterations_run / secs,
+               "gemv_ms": ms, "gemv_GBps_per_gpu": 4.0 * rows * nn / ms / 1e6, "gemv_launches_timed": int(r.gemv_launches_timed),
+               "note": "opt-in storage mode, not the headline metric: fp32 matrix block, everything else fp64"}
+        sv.close()
+        if rank == 0:
+            import oracle
+            o = oracle.cg_solve_generated(nn, k, 1e-9)
+            out.update(oracle_iterations=int(o.iters), oracle_rel_residual=o.rel, x_rel_l2_vs_oracle=rel_l2(x, o.x), bound=1e-12)
+            out["ok"] = bool(out["iterations"] == o.iters and out["x_rel_l2_vs_oracle"] <= 1e-12 and out["entries_rounded"] == 0)
+        return out
+
     configs = {}
+    mixed = None
     if not args.no_extras:
+        if args.gemv_variant in (0, 32, 36):
+            mixed = mixed_storage_case(n, iters)
         rem = generate_case(n + 3, 30, 1e-12)
         ing = file_case(1501, 60, 256 << 10, 4)
         if rank == 0:
@@ -533,6 +566,8 @@ def run_b200_arm(args):
         }
         if configs:
             line["configs"] = configs
+        if mixed is not None:
+            line["matrix_f32"] = mixed
         if ref_gpu is not None:
             line["reference_gpu"] = ref_gpu
         if world == 1 and not args.no_cpu_baseline:

@@ -71,6 +71,10 @@ typedef struct {
     int dtype;          /* 0 fp64, 1 fp32 */
     int ingest_threads; /* reader threads and ... */
     int ingest_chunks;  /* ... staging chunks the last lamcg_load_matrix used on this rank */
+    int matrix_elem_bytes; /* bytes per matrix element in HBM: 8 / 4 by dtype, 4 on an fp64 handle under option matrix_f32 */
+    unsigned long long matrix_f32_inexact;  /* option matrix_f32: entries of the last matrix this rank took in whose fp32 value differs
+                                               from the fp64 source (0: the solve runs on exactly the caller's matrix) ... */
+    unsigned long long matrix_f32_overflow; /* ... and finite entries that became infinite */
 } lamcg_info;
 
 /* ---- lifetime ------------------------------------------------------------------------------ */
@@ -99,6 +103,14 @@ const char *lamcg_version(void);
  *  persist_grid  upper bound on the CTAs of the persistent kernel (0: one per SM)
  *  fuse_updates  1 (default): K2 + K3 as one cooperative launch (single rank / peer mode); 0: two launches
  *  loop_profile  1: stream / graph loop in peer mode: CTA 0 accumulates wait and work cycles per phase (lamcg_get_loop_profile)
+ *  matrix_f32    1 (fp64 handles; default 0, OPT-IN because it changes the problem being solved): the matrix block is held in HBM as
+ *                fp32 while b, x, r, p, Ap, every product, sum and scalar stay fp64 (the reference instantiates <float>,
+ *                GPU_MPI.cu:707; this is the mixed form).  K1 widens each element (exact) and then runs the fp64 sweep's unfused
+ *                multiply + add, so the solve is the fp64 solve of fl32(A) at half the HBM bytes per iteration.  A matrix whose
+ *                entries are fp32 numbers (generate mode: 0, 1, 2) is solved as given; otherwise lamcg_info.matrix_f32_inexact
+ *                says how many entries were rounded.  Callers and files still hold doubles (narrowed on the device during
+ *                set_matrix / load_matrix).  Changing the option drops the loaded system.  Row sweeps 32 / 36 and the stream /
+ *                graph loops only; the one-kernel loop, the SPD generator and save_system need it off.
  *  spd_simt      1: the SPD generator as in round 1 (SIMT products, recursion to single columns); 0 (default): DMMA + CholeskyQR2 leaves
  *  chunk_iters   iterations per graph launch
  *  time_gemv     1: CUDA events around every GEMV launch (stream loop; with loop_mode 2 as event-record nodes inside the graph);

@@ -31,11 +31,13 @@ def main():
     report = {"comm": comm, "world": world, "cases": []}
     ok = True
 
-    def case(name, n, make_system, max_iters, loop_mode, tol, dtype="f64"):
+    def case(name, n, make_system, max_iters, loop_mode, tol, dtype="f64", options=()):
         nonlocal ok
         s = lamcg_b200.Solver(local, rank, world, dtype)
         lamcg_b200.launch.bootstrap_comm(s, n=n, mode=comm, dist=dist)
         s.set_option("loop_mode", loop_mode)
+        for key, value in options:
+            s.set_option(key, value)
         ref = make_system(s)
         r = s.solve(max_iters, 1e-9)
         x = s.solution()                   # collective gather through the library
@@ -73,8 +75,19 @@ def main():
             return oracle.cg_solve_generated(n, max_iters, 1e-9)
         return mk
 
-    def spd(n, seed):
+    def spd(n, seed, through_fp32=False):
         A, b = random_spd.random_spd_system(n, seed)
+        if through_fp32:  # option matrix_f32: the library is handed A and must behave like the fp64 solve of fl32(A)
+            A_given, A = A, A.astype(np.float32).astype(np.float64)
+
+            def mk32(s):
+                s.set_matrix(A_given)
+                s.set_rhs(b)
+                assert s.info.matrix_elem_bytes == 4 and s.info.matrix_f32_inexact > 0
+                o = oracle.cg_solve(A, b, 1000, 1e-9)
+                o.A, o.b = A, b
+                return o
+            return mk32
 
         def mk(s):
             s.set_matrix(A)          # layout 0: every rank is handed the whole matrix and takes its rows
@@ -197,6 +210,10 @@ def main():
     case("spd_file", 1024, spd(1024, 11), 1000, 2, 1e-9)  # stops may differ by an iteration: see tests/test_gpu_parity.py X_TOL_STOPPED
     case("gen_big", 40000, gen(40000, 100), 100, 2, 1e-12)
     case("gen_f32", 4100, gen(4100, 120), 120, 2, 1e-4, dtype="f32")  # fp32 storage across ranks (p slices, x gather in floats)
+
+    # option matrix_f32 across ranks: the fp32 row blocks are local, the exchanged vectors stay fp64
+    case("gen_mixed_remainder", 10007, gen(10007, 200), 200, 2, 1e-12, options=(("matrix_f32", 1),))
+    case("spd_mixed", 1024, spd(1024, 11, through_fp32=True), 1000, 2, 1e-9, options=(("matrix_f32", 1),))
 
     if comm == "peer" and world == 2:
         case_peer_timeout()

@@ -59,7 +59,11 @@ def test_library_is_sm100a_native_code(lamcg):
         assert len(names) == 1, (fragment, names)
         return ks[names[0]]
 
-    for frag in ("rowsweep_kernelIdLi8ELi4ELi512ELi1ELi16E", "rowsweep_kernelIdLi8ELi4ELi256ELi2ELi16E"):  # variants 36 / 32 (defaults)
+    for frag in ("rowsweep_kernelIdLi8ELi4ELi512ELi1ELi16EfE", "rowsweep_kernelIdLi8ELi4ELi256ELi2ELi16EfE"):  # option matrix_f32
+        loop = S.mix(S.main_loop(one(frag)))  # fp32 matrix, everything else fp64: 4 columns per load, each widened exactly
+        assert loop["LDG.E.NA.128.CONSTANT"] == 32 and loop["LDG.E.ENL2.256.CONSTANT"] == 4, loop
+        assert loop["F2F.F64.F32"] == 128 and loop["DMUL"] == 128 and loop["DADD"] == 128 and loop.get("DFMA", 0) == 0, loop
+    for frag in ("rowsweep_kernelIdLi8ELi4ELi512ELi1ELi16EdE", "rowsweep_kernelIdLi8ELi4ELi256ELi2ELi16EdE"):  # variants 36 / 32 (defaults)
         k = one(frag)
         loop = S.mix(S.main_loop(k))
         assert loop["LDG.E.NA.128.CONSTANT"] == 32 and loop["LDG.E.128.CONSTANT"] == 4, loop   # A: 8 rows x 4; p: 4
@@ -68,7 +72,7 @@ def test_library_is_sm100a_native_code(lamcg):
         whole = S.mix(k)
         assert not any(op.startswith(("STL", "LDL")) for op in whole), "register spills in the default K1"
         assert not any("UBLKCP" in op for op in whole)
-    for frag in ("rowsweep_kernelIdLi8ELi2ELi512ELi1ELi32E", "rowsweep_kernelIdLi8ELi2ELi256ELi2ELi32E"):  # variants 46 / 42
+    for frag in ("rowsweep_kernelIdLi8ELi2ELi512ELi1ELi32EdE", "rowsweep_kernelIdLi8ELi2ELi256ELi2ELi32EdE"):  # variants 46 / 42
         loop = S.mix(S.main_loop(one(frag)))
         assert loop["LDG.E.NA.ENL2.256.CONSTANT"] == 16, loop
     for frag in ("lamcg_tmaring_kernel", "lamcg_warprows_tmap_kernel"):
