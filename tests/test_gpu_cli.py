@@ -43,6 +43,19 @@ def test_generate_mode_csv_line_matches_reference_rows(golden, tmp_path):
         assert np.linalg.norm(x - o.x) / np.linalg.norm(o.x) <= 1e-12  # we save x (the reference saves b: defect 2)
 
 
+def test_generate_mode_with_the_matrix_held_in_fp32_by_environment(golden, tmp_path):
+    """LAMCG_MATRIX_F32=1 switches the unmodified driver to the mixed storage (option matrix_f32); generate mode's 0 / 1 / 2 are fp32
+    numbers, so iteration count, printed residual and x are those of the reference all the same."""
+    g = [e for e in golden["generate_mode_cli"] if e["n"] == 10000 and e["max_iters"] == 15][0]
+    res = run([GETOPT, "-s", str(g["n"]), "-i", str(g["max_iters"]), "-e", "1e-9", "-o", str(tmp_path / "sol.bin")], env={"LAMCG_MATRIX_F32": "1"})
+    assert res.returncode == 0, res.stderr
+    f = res.stdout.strip().split(",")
+    assert len(f) == 9 and int(f[6]) == g["iters"] and math.isclose(float(f[7]), g["rel_printed"], rel_tol=2e-5)
+    x = fileformat.read_vector(str(tmp_path / "sol.bin"))
+    o = oracle.cg_solve_generated(g["n"], g["max_iters"], 1e-9)
+    assert np.linalg.norm(x - o.x) / np.linalg.norm(o.x) <= 1e-12
+
+
 @pytest.mark.parametrize("exe,fields", [(GETOPT, 9), (GETOPT_NCCL, 10)])
 def test_csv_field_count_per_executable(exe, fields, tmp_path):
     """The reference ships two getopt GPU executables whose CSV lines differ by one field: test_CG_MultiGPUS_CUDA_MPI.out prints
